@@ -1,0 +1,168 @@
+/*
+ * metrpo.h -- C ABI of the B200-native ME-TRPO hot path (libmetrpo.so).
+ *
+ * The reference (thanard/me-trpo) is pure Python + TF 1.4 and has no FFI; its "plugin API" for
+ * the imaginary-rollout path is three duck-typed Python sockets.  Each entry
+ * point below names the reference interface it replaces (file:line under the reference tree).
+ * The Python classes in me_trpo_b200/ that mirror those sockets bind these symbols via ctypes
+ * (me_trpo_b200/lib.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer argument is a DEVICE pointer on the handle's device unless it says "host";
+ *     the caller (torch) owns all buffers, the library owns only the handle, its packed weight
+ *     images and its workspace;
+ *   - every call is asynchronous on the passed cudaStream_t (as void*), no implicit sync;
+ *   - returns 0 (METRPO_OK) or a negative metrpo_status_t; message via metrpo_last_error()
+ *     (thread-local).  Nothing throws or aborts across the ABI;
+ *   - a handle is bound to one device and is not thread-safe; distinct handles are independent;
+ *   - weights use the reference's TF layout: W[in, out] row-major, y = x @ W + b
+ *     (training.py:187-208);
+ *   - there is no CPU fallback: on a device that is not sm_100 create() fails.
+ */
+#ifndef METRPO_H_
+#define METRPO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  METRPO_OK = 0,
+  METRPO_ERR_INVALID = -1,     /* bad argument / shape */
+  METRPO_ERR_CUDA = -2,        /* a CUDA runtime call failed (message has the cudaError) */
+  METRPO_ERR_UNSUPPORTED = -3, /* valid reference config this build does not cover yet */
+  METRPO_ERR_NOMEM = -4,
+  METRPO_ERR_STATE = -5        /* call order (e.g. run before weights were set) */
+} metrpo_status_t;
+
+/* envs whose analytic cost / done the kernel fuses (envs/com_*_env.py cost_np_vec / is_done) */
+enum {
+  METRPO_ENV_SWIMMER = 0,      /* com_swimmer_env.py:112-114 */
+  METRPO_ENV_HALF_CHEETAH = 1, /* com_half_cheetah_env.py:72-75 */
+  METRPO_ENV_HOPPER = 2,       /* com_hopper_env.py:94-104 */
+  METRPO_ENV_ANT = 3,          /* com_ant_env.py:77-101 (cost + is_done) */
+  METRPO_ENV_HUMANOID = 4,     /* com_simple_humanoid_env.py:105-109 */
+  METRPO_ENV_SNAKE = 5         /* com_snake_env.py:81-84 */
+};
+
+/* VecSimpleEnv.get_next_observation sam_mode (env_helpers.py:617-634) */
+enum {
+  METRPO_SAM_STEP_RAND = 0,     /* per-row random model every step */
+  METRPO_SAM_EPS_RAND = 1,      /* per-episode model (cur_model_idx) */
+  METRPO_SAM_MODEL_MEAN_STD = 2,
+  METRPO_SAM_MODEL_MEAN = 3,
+  METRPO_SAM_MODEL_MED = 4,
+  METRPO_SAM_ONE_MODEL = 5
+};
+
+enum { METRPO_PREC_BF16 = 0 }; /* tensor-core input type; accumulation and epilogues are fp32 */
+
+#define METRPO_MAX_POLICY_LAYERS 4
+
+typedef struct {
+  int32_t state_dim;        /* S */
+  int32_t action_dim;       /* A */
+  int32_t drop_cols;        /* 0 none, 1 ignore_x_input, 2 ignore_xy_input (training.py:146-154) */
+  int32_t hidden;           /* dynamics hidden width; both hidden layers (params/*.json) */
+  int32_t n_models;         /* K (params "n_models") */
+  int32_t n_envs;           /* B parallel imaginary envs (rows) */
+  int32_t max_path_length;  /* T: timeout horizon (env_helpers.py:604) */
+  int32_t env_id;           /* METRPO_ENV_* */
+  int32_t sam_mode;         /* METRPO_SAM_* */
+  int32_t n_policy_layers;  /* number of policy weight matrices (hidden layers + 1) */
+  int32_t policy_dims[METRPO_MAX_POLICY_LAYERS + 1]; /* S, h1, .., A */
+  int32_t policy_out_tanh;  /* policy output_nonlinearity: 0 tf.identity, 1 tf.tanh */
+  int32_t precision;        /* METRPO_PREC_* */
+  int32_t device;           /* CUDA device ordinal */
+} metrpo_rollout_cfg;
+
+typedef struct metrpo_rollout metrpo_rollout_t;
+
+/* library / build info string (static storage) */
+const char* metrpo_version(void);
+/* message of the last failing call on this thread (static thread-local storage) */
+const char* metrpo_last_error(void);
+
+/* Handle for one imaginary vec-env = one NeuralNetEnv + VecSimpleEnv pair
+ * (env_helpers.py:532-544, 575-583). */
+int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollout_t** out);
+int metrpo_rollout_destroy(metrpo_rollout_t* h);
+
+/* Stage model k of the ensemble: the weights of build_ff_neural_net (training.py:171-214),
+ * fp32, TF layout.  W0[Din,H] b0[H] W1[H,H] b1[H] W2[H,S] b2[S], Din = S + A - drop_cols.
+ * Packs them into the bf16 tile stream the persistent kernel bulk-copies every step. */
+int metrpo_rollout_set_dynamics(metrpo_rollout_t* h, int k, const float* W0, const float* b0,
+                                const float* W1, const float* b1, const float* W2,
+                                const float* b2, void* stream);
+
+/* RunningMeanStd constants (running_mean_std.py:22-27) used by dynamics_model
+ * (training.py:228,257): in_mean/in_std [S+A], diff_mean/diff_std [S]. */
+int metrpo_rollout_set_normalization(metrpo_rollout_t* h, const float* in_mean,
+                                     const float* in_std, const float* diff_mean,
+                                     const float* diff_std, void* stream);
+
+/* Gaussian MLP policy mean network + log_std (training.py:96-117; rllab GaussianMLPPolicy).
+ * W[i] is [policy_dims[i], policy_dims[i+1]], b[i] is [policy_dims[i+1]]; W, b are HOST arrays
+ * of n_policy_layers DEVICE pointers; log_std is a device vector [A]. */
+int metrpo_rollout_set_policy(metrpo_rollout_t* h, const float* const* W, const float* const* b,
+                              const float* log_std, void* stream);
+
+/* VecSimpleEnv.reset() with explicit states (env_helpers.py:585-595): states[B,S] become the
+ * current observations, ts = 0.  The reference draws them from the real simulator. */
+int metrpo_rollout_reset(metrpo_rollout_t* h, const float* states, void* stream);
+
+/* VecSimpleEnv.step (env_helpers.py:597-607), socket B1.  actions[B,A] are the sampler's
+ * UNCLIPPED actions; the kernel clips to [-1,1] (:599), evaluates all K models (:612-615),
+ * selects per sam_mode, computes reward = -cost_np_vec (:601), done = is_done | ts >= T (:603-604)
+ * and replaces done rows by reset_states[row] (:605-606).
+ *   model_idx  [B] int32 or NULL: step_rand / eps_rand choice per row (NULL -> Philox(seed,offset))
+ *   std_noise  [B,S] or NULL: N(0,1) draws for model_mean_std (:626)
+ *   reset_states [B,S]: row i takes reset_states[i] if it finishes this step
+ *   obs_out [B,S] post-reset observations, rew_out [B], done_out [B] uint8. */
+int metrpo_rollout_step(metrpo_rollout_t* h, const float* actions, const int32_t* model_idx,
+                        const float* std_noise, const float* reset_states, uint64_t seed,
+                        uint64_t offset, float* obs_out, float* rew_out, uint8_t* done_out,
+                        void* stream);
+
+/* VectorizedSampler.obtain_samples (samplers/vectorized_sampler.py:45-116) for n_steps steps of
+ * all B rows, socket B2: one persistent kernel runs policy -> K dynamics -> select -> reward /
+ * done / reset -> trajectory write for the whole horizon with no host round trip.
+ *   init_states [B,S]   observations after the initial vec_env.reset() (:49)
+ *   reset_pool  [R,S]   pre-sampled real-env reset states; the n-th reset (n = 0,1,..) of row i
+ *                       takes reset_pool[(n*B + i) % R]  (reference order when all rows time out
+ *                       together; see DESIGN.md for Ant)
+ *   eps         [n_steps,B,A] N(0,1) policy noise or NULL -> Philox(seed, offset) on device
+ *   model_idx   [n_steps,B] int32 or NULL -> Philox
+ *   std_noise   [n_steps,B,S] or NULL (model_mean_std only; NULL -> Philox)
+ *   determ      1 -> actions = mean (obtain_samples(determ=True), :64-65)
+ * outputs (any may be NULL to skip the write), time-major:
+ *   obs [n_steps,B,S] pre-step observations (:91), act [n_steps,B,A] UNCLIPPED actions (:92),
+ *   mean [n_steps,B,A] agent_infos['mean'], rew [n_steps,B], done [n_steps,B] uint8,
+ *   final_states [B,S] observations after the last step (post-reset). */
+int metrpo_rollout_run(metrpo_rollout_t* h, int n_steps, const float* init_states,
+                       const float* reset_pool, int R, const float* eps,
+                       const int32_t* model_idx, const float* std_noise, uint64_t seed,
+                       uint64_t offset, int determ, float* obs, float* act, float* mean,
+                       float* rew, uint8_t* done, float* final_states, void* stream);
+
+/* Synchronise the stream and report the outcome of the last launch: METRPO_OK, or METRPO_ERR_STATE
+ * with a message naming the stalled barrier if the kernel's bounded waits timed out (the kernel
+ * aborts itself instead of hanging the GPU). */
+int metrpo_rollout_status(metrpo_rollout_t* h, void* stream);
+
+/* number of kernels the last run()/step() call launched on the stream (bench gpu_launches) */
+int metrpo_rollout_last_launches(const metrpo_rollout_t* h);
+
+/* Single-CTA tcgen05 GEMM self-test: C[128,N] = A[128,K] * B[N,K]^T (bf16 in, fp32 out) through
+ * the same descriptors the rollout kernel uses.  mode 0: SW128 smem operands, B by bulk copy;
+ * 1: no-swizzle core-matrix operands; 2: A in TMEM.  cycles (device, may be NULL) receives the
+ * clock64 span of `reps` back-to-back K loops. */
+int metrpo_selftest_umma(int mode, int N, int K, int reps, const void* A_bf16, const void* B_bf16,
+                         float* C, unsigned long long* cycles, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METRPO_H_ */

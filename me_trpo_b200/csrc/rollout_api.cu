@@ -1,0 +1,485 @@
+// C-ABI entry points of the ensemble-rollout path (include/metrpo.h): handle management, weight
+// packing into the bf16 tile stream, gang schedule construction and kernel launch.
+#include <cstring>
+#include <map>
+#include <vector>
+#include <algorithm>
+
+#include "common.cuh"
+#include "rollout_kernel.cuh"
+
+namespace metrpo {
+
+// ---------------------------------------------------------------------------------------------
+// packing kernels (one thread per destination element)
+// ---------------------------------------------------------------------------------------------
+// stage (nc,kc) = [ W1 tile: n in [256nc,+256) x k in [64kc,+64), SW128 | W0 tile (kc+2)%KC ]
+__global__ void pack_w1_kernel(const float* __restrict__ W1, uint8_t* __restrict__ dst, int H,
+                               int KC, uint32_t stage_bytes) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<size_t>(H) * H) return;
+  const int kglob = static_cast<int>(i / H), n = static_cast<int>(i % H);   // W1[k][n]
+  const int nc = n / 256, nl = n % 256, kc = kglob / 64, kl = kglob % 64;
+  uint8_t* st = dst + static_cast<size_t>(nc * KC + kc) * stage_bytes;
+  *reinterpret_cast<__nv_bfloat16*>(st + sw128_off(nl, kl)) = __float2bfloat16_rn(W1[i]);
+}
+// W0 tile j: n in [64j,+64) x k in [0,K0), no-swizzle core-matrix layout, zero padded k >= Din
+__global__ void pack_w0_kernel(const float* __restrict__ W0, uint8_t* __restrict__ dst, int H,
+                               int Din, int K0, int NC, int KC, uint32_t stage_bytes,
+                               uint32_t w0tile_bytes, uint32_t off_w0res) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K0 * H) return;
+  const int kk = i / H, n = i % H;
+  const int j = n / 64, nl = n % 64;
+  const __nv_bfloat16 v = __float2bfloat16_rn(kk < Din ? W0[kk * H + n] : 0.f);
+  const uint32_t off = noswz_off(nl, kk, 64);
+  // tile j rides in the stage whose kc satisfies (kc + 2) % KC == j, in every nc pass
+  const int kc = (j + KC - 2) % KC;
+  for (int nc = 0; nc < NC; ++nc) {
+    uint8_t* st = dst + static_cast<size_t>(nc * KC + kc) * stage_bytes + W1_TILE_BYTES;
+    *reinterpret_cast<__nv_bfloat16*>(st + off) = v;
+  }
+  if (j < 2) *reinterpret_cast<__nv_bfloat16*>(dst + off_w0res + j * w0tile_bytes + off) = v;
+}
+// W2 chunk nc: 4 sub-tiles [S_pad rows (s)][64 k] SW128, zero padded s >= S
+__global__ void pack_w2_kernel(const float* __restrict__ W2, uint8_t* __restrict__ dst, int H, int S,
+                               int S_pad, uint32_t off_w2, uint32_t w2chunk_bytes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * S_pad) return;
+  const int h = i / S_pad, s = i % S_pad;
+  const int nc = h / 256, sub = (h % 256) / 64, kl = h % 64;
+  const float v = s < S ? W2[h * S + s] : 0.f;
+  uint8_t* base = dst + off_w2 + static_cast<size_t>(nc) * w2chunk_bytes + sub * (S_pad * 128);
+  *reinterpret_cast<__nv_bfloat16*>(base + sw128_off(s, kl)) = __float2bfloat16_rn(v);
+}
+__global__ void pack_bias_kernel(const float* __restrict__ b0, const float* __restrict__ b1,
+                                 const float* __restrict__ b2, float* __restrict__ dst, int H, int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * H + 32) return;
+  dst[i] = i < H ? b0[i] : (i < 2 * H ? b1[i - H] : (i - 2 * H < S ? b2[i - 2 * H] : 0.f));
+}
+__global__ void pack_policy_layer_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                                         float* __restrict__ dst_w, float* __restrict__ dst_b, int nin,
+                                         int nout, int npad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nin * npad) {
+    const int r = i / npad, c = i % npad;
+    dst_w[i] = c < nout ? W[r * nout + c] : 0.f;
+  }
+  if (i < npad) dst_b[i] = i < nout ? b[i] : 0.f;
+}
+__global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n,
+                                float pad, int npad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npad) dst[i] = i < n ? src[i] : pad;
+}
+__global__ void reset_rows_kernel(const float* __restrict__ states, float* __restrict__ row_state,
+                                  int* __restrict__ row_ts, int* __restrict__ row_nreset, int B, int S,
+                                  int rows_padded) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * S) row_state[i] = states[i];
+  if (i < rows_padded) { row_ts[i] = 0; row_nreset[i] = 0; }
+}
+
+}  // namespace metrpo
+
+using namespace metrpo;
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct metrpo_rollout {
+  metrpo_rollout_cfg cfg;
+  int Din, K0, S_pad, NC, KC, n_tiles, max_slots, num_sms;
+  uint32_t stage_bytes, w0tile_bytes, w2chunk_bytes, off_w2, off_w0res;
+  size_t model_stride;
+  // device buffers
+  uint8_t* wstream = nullptr;
+  float* bias = nullptr;
+  float* norm = nullptr;
+  float* pol = nullptr;
+  float* xbuf = nullptr;
+  unsigned* xctr = nullptr;
+  float* row_state = nullptr;
+  int* row_ts = nullptr;
+  int* row_nreset = nullptr;
+  unsigned* tile_flag = nullptr;
+  unsigned* dbg = nullptr;
+  int dbg_words = 0;
+  std::map<int, int4*> schedules;   // n_steps -> device [max_slots][MAX_SEG]
+  std::map<int, int> schedule_slots;
+  // policy blob meta
+  PolicyLayer pl[4];
+  int pol_floats = 0, pol_logstd_off = 0;
+  // smem layout
+  uint32_t off_stage, off_sw0res, off_z, off_h0, off_h1, off_sw2, off_sbias, off_snorm, off_spol,
+      off_bars, smem_bytes;
+  std::vector<char> dyn_set;
+  bool norm_set = false, pol_set = false, state_set = false;
+  int last_launches = 0;
+};
+
+static uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+static void free_handle(metrpo_rollout* h) {
+  if (!h) return;
+  cudaFree(h->wstream); cudaFree(h->bias); cudaFree(h->norm); cudaFree(h->pol); cudaFree(h->xbuf);
+  cudaFree(h->xctr); cudaFree(h->row_state); cudaFree(h->row_ts); cudaFree(h->row_nreset);
+  cudaFree(h->tile_flag); cudaFree(h->dbg);
+  for (auto& kv : h->schedules) cudaFree(kv.second);
+  delete h;
+}
+
+extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollout_t** out) {
+  if (!cfg || !out) return set_error(METRPO_ERR_INVALID, "create: null argument");
+  *out = nullptr;
+  const metrpo_rollout_cfg& c = *cfg;
+  if (c.state_dim < 2 || c.action_dim < 1 || c.n_models < 1 || c.n_envs < 1 || c.max_path_length < 1)
+    return set_error(METRPO_ERR_INVALID, "create: S>=2, A>=1, K>=1, B>=1, T>=1 required");
+  if (c.drop_cols < 0 || c.drop_cols > 2 || c.drop_cols >= c.state_dim)
+    return set_error(METRPO_ERR_INVALID, "create: drop_cols must be 0, 1 or 2");
+  if (c.env_id < METRPO_ENV_SWIMMER || c.env_id > METRPO_ENV_SNAKE)
+    return set_error(METRPO_ERR_INVALID, "create: unknown env_id %d", c.env_id);
+  if (c.sam_mode < METRPO_SAM_STEP_RAND || c.sam_mode > METRPO_SAM_ONE_MODEL)
+    return set_error(METRPO_ERR_INVALID, "create: unknown sam_mode %d", c.sam_mode);
+  if (c.precision != METRPO_PREC_BF16)
+    return set_error(METRPO_ERR_UNSUPPORTED, "create: only METRPO_PREC_BF16 is implemented");
+  if (c.hidden < 256 || c.hidden % 256)
+    return set_error(METRPO_ERR_UNSUPPORTED, "create: dynamics hidden width must be a multiple of 256 (got %d)", c.hidden);
+  if (c.state_dim > SMAX || c.action_dim > AMAX)
+    return set_error(METRPO_ERR_UNSUPPORTED, "create: this build covers S <= %d, A <= %d (got %d, %d)", SMAX, AMAX, c.state_dim, c.action_dim);
+  if (c.n_policy_layers < 1 || c.n_policy_layers > METRPO_MAX_POLICY_LAYERS)
+    return set_error(METRPO_ERR_INVALID, "create: n_policy_layers in [1,%d]", METRPO_MAX_POLICY_LAYERS);
+  if (c.policy_dims[0] != c.state_dim || c.policy_dims[c.n_policy_layers] != c.action_dim)
+    return set_error(METRPO_ERR_INVALID, "create: policy_dims must run from S to A");
+  for (int l = 1; l < c.n_policy_layers; ++l)
+    if (c.policy_dims[l] < 1 || c.policy_dims[l] > HPMAX)
+      return set_error(METRPO_ERR_UNSUPPORTED, "create: policy hidden width <= %d in this build", HPMAX);
+  // env-specific index requirements of the fused cost (envs/com_*_env.py)
+  const int need_s[] = {6, 10, 6, 16, 1, 8};
+  if (c.state_dim < need_s[c.env_id])
+    return set_error(METRPO_ERR_INVALID, "create: env %d needs state_dim >= %d", c.env_id, need_s[c.env_id]);
+
+  METRPO_CUDA_OK(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  METRPO_CUDA_OK(cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major != 10)
+    return set_error(METRPO_ERR_UNSUPPORTED, "create: device %d is sm_%d%d; this library is sm_100a only (no fallback)", c.device, prop.major, prop.minor);
+  if (c.n_models > prop.multiProcessorCount)
+    return set_error(METRPO_ERR_UNSUPPORTED, "create: n_models > SM count");
+
+  metrpo_rollout* h = new metrpo_rollout();
+  h->cfg = c;
+  h->num_sms = prop.multiProcessorCount;
+  h->Din = c.state_dim + c.action_dim - c.drop_cols;
+  h->K0 = static_cast<int>(align_up(h->Din, 16));
+  h->S_pad = static_cast<int>(align_up(c.state_dim, 16));
+  h->NC = c.hidden / 256;
+  h->KC = c.hidden / 64;
+  h->n_tiles = (c.n_envs + TILE_M - 1) / TILE_M;
+  h->max_slots = std::min(h->n_tiles, h->num_sms / c.n_models);
+  h->w0tile_bytes = 64 * h->K0 * 2;
+  h->stage_bytes = W1_TILE_BYTES + h->w0tile_bytes;
+  h->w2chunk_bytes = h->S_pad * 256 * 2;
+  h->off_w2 = h->NC * h->KC * h->stage_bytes;
+  h->off_w0res = h->off_w2 + h->NC * h->w2chunk_bytes;
+  h->model_stride = align_up(h->off_w0res + 2 * h->w0tile_bytes, 1024);
+  h->dyn_set.assign(c.n_models, 0);
+
+  // policy blob layout
+  int off = 0;
+  for (int l = 0; l < c.n_policy_layers; ++l) {
+    PolicyLayer& L = h->pl[l];
+    L.nin = c.policy_dims[l];
+    L.nout = c.policy_dims[l + 1];
+    L.npad = (l == c.n_policy_layers - 1) ? AMAX : HPMAX;
+    L.w_off = off; off += L.nin * L.npad;
+    L.b_off = off; off += L.npad;
+  }
+  h->pol_logstd_off = off; off += AMAX;
+  h->pol_floats = off;
+
+  // shared-memory carve-up
+  uint32_t o = 0;
+  h->off_stage = o; o += NSTAGE * h->stage_bytes;
+  h->off_sw0res = o; o += 2 * h->w0tile_bytes;
+  h->off_z = o; o += TILE_M * h->K0 * 2;
+  o = align_up(o, 1024); h->off_h0 = o; o += 2 * H_TILE_BYTES;
+  h->off_h1 = o; o += 2 * H_TILE_BYTES;
+  h->off_sw2 = o; o += h->w2chunk_bytes;
+  h->off_sbias = o; o += (2 * c.hidden + 32) * 4;
+  h->off_snorm = o; o += align_up((2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4, 16);
+  h->off_spol = o; o += align_up(h->pol_floats * 4, 16);
+  h->off_bars = o; o += NUM_BARS * 8;
+  h->smem_bytes = o + 1024;
+  if (h->smem_bytes > static_cast<uint32_t>(prop.sharedMemPerBlockOptin)) {
+    int need = h->smem_bytes;
+    delete h;
+    return set_error(METRPO_ERR_UNSUPPORTED, "create: config needs %d B of shared memory per CTA (limit %d)", need, (int)prop.sharedMemPerBlockOptin);
+  }
+  if ((c.state_dim + c.action_dim) * TILE_M * 4 > 2 * H_TILE_BYTES) {
+    delete h;
+    return set_error(METRPO_ERR_UNSUPPORTED, "create: S + A too large for the scratch tiles");
+  }
+
+  const size_t rows_pad = static_cast<size_t>(h->n_tiles) * TILE_M;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
+  };
+  alloc(reinterpret_cast<void**>(&h->wstream), h->model_stride * c.n_models);
+  alloc(reinterpret_cast<void**>(&h->bias), static_cast<size_t>(c.n_models) * (2 * c.hidden + 32) * 4);
+  alloc(reinterpret_cast<void**>(&h->norm), (2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4);
+  alloc(reinterpret_cast<void**>(&h->pol), h->pol_floats * 4);
+  alloc(reinterpret_cast<void**>(&h->xbuf), static_cast<size_t>(h->max_slots) * 2 * c.n_models * c.state_dim * TILE_M * 4);
+  alloc(reinterpret_cast<void**>(&h->xctr), h->max_slots * 4);
+  alloc(reinterpret_cast<void**>(&h->row_state), rows_pad * c.state_dim * 4);
+  alloc(reinterpret_cast<void**>(&h->row_ts), rows_pad * 4);
+  alloc(reinterpret_cast<void**>(&h->row_nreset), rows_pad * 4);
+  alloc(reinterpret_cast<void**>(&h->tile_flag), h->n_tiles * 4);
+  h->dbg_words = DBG_HEADER + h->max_slots * c.n_models * (NUM_THREADS / 32) * DBG_WORDS_PER_WARP;
+  alloc(reinterpret_cast<void**>(&h->dbg), h->dbg_words * 4);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+  if (e != cudaSuccess) {
+    free_handle(h);
+    return set_error(e == cudaErrorMemoryAllocation ? METRPO_ERR_NOMEM : METRPO_ERR_CUDA, "create: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_rollout_destroy(metrpo_rollout_t* h) {
+  if (!h) return METRPO_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  free_handle(h);
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_rollout_set_dynamics(metrpo_rollout_t* h, int k, const float* W0, const float* b0,
+                                           const float* W1, const float* b1, const float* W2,
+                                           const float* b2, void* stream_) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "set_dynamics: null handle");
+  if (k < 0 || k >= h->cfg.n_models) return set_error(METRPO_ERR_INVALID, "set_dynamics: model index %d out of range", k);
+  if (!W0 || !b0 || !W1 || !b1 || !W2 || !b2) return set_error(METRPO_ERR_INVALID, "set_dynamics: null weight pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int H = h->cfg.hidden, S = h->cfg.state_dim;
+  uint8_t* dst = h->wstream + static_cast<size_t>(k) * h->model_stride;
+  const int T = 256;
+  pack_w1_kernel<<<(static_cast<size_t>(H) * H + T - 1) / T, T, 0, st>>>(W1, dst, H, h->KC, h->stage_bytes);
+  pack_w0_kernel<<<(h->K0 * H + T - 1) / T, T, 0, st>>>(W0, dst, H, h->Din, h->K0, h->NC, h->KC,
+                                                        h->stage_bytes, h->w0tile_bytes, h->off_w0res);
+  pack_w2_kernel<<<(H * h->S_pad + T - 1) / T, T, 0, st>>>(W2, dst, H, S, h->S_pad, h->off_w2, h->w2chunk_bytes);
+  pack_bias_kernel<<<(2 * H + 32 + T - 1) / T, T, 0, st>>>(b0, b1, b2, h->bias + static_cast<size_t>(k) * (2 * H + 32), H, S);
+  METRPO_CUDA_OK(cudaGetLastError());
+  h->dyn_set[k] = 1;
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_rollout_set_normalization(metrpo_rollout_t* h, const float* in_mean,
+                                                const float* in_std, const float* diff_mean,
+                                                const float* diff_std, void* stream_) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "set_normalization: null handle");
+  if (!in_mean || !in_std || !diff_mean || !diff_std) return set_error(METRPO_ERR_INVALID, "set_normalization: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int SA = h->cfg.state_dim + h->cfg.action_dim, S = h->cfg.state_dim;
+  METRPO_CUDA_OK(cudaMemcpyAsync(h->norm, in_mean, SA * 4, cudaMemcpyDeviceToDevice, st));
+  METRPO_CUDA_OK(cudaMemcpyAsync(h->norm + SA, in_std, SA * 4, cudaMemcpyDeviceToDevice, st));
+  METRPO_CUDA_OK(cudaMemcpyAsync(h->norm + 2 * SA, diff_mean, S * 4, cudaMemcpyDeviceToDevice, st));
+  METRPO_CUDA_OK(cudaMemcpyAsync(h->norm + 2 * SA + S, diff_std, S * 4, cudaMemcpyDeviceToDevice, st));
+  h->norm_set = true;
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_rollout_set_policy(metrpo_rollout_t* h, const float* const* W, const float* const* b,
+                                         const float* log_std, void* stream_) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "set_policy: null handle");
+  if (!W || !b || !log_std) return set_error(METRPO_ERR_INVALID, "set_policy: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  for (int l = 0; l < h->cfg.n_policy_layers; ++l) {
+    if (!W[l] || !b[l]) return set_error(METRPO_ERR_INVALID, "set_policy: null layer %d", l);
+    const PolicyLayer& L = h->pl[l];
+    const int n = std::max(L.nin * L.npad, L.npad);
+    pack_policy_layer_kernel<<<(n + 255) / 256, 256, 0, st>>>(W[l], b[l], h->pol + L.w_off, h->pol + L.b_off,
+                                                              L.nin, L.nout, L.npad);
+  }
+  copy_f32_kernel<<<1, 32, 0, st>>>(log_std, h->pol + h->pol_logstd_off, h->cfg.action_dim, 0.f, AMAX);
+  METRPO_CUDA_OK(cudaGetLastError());
+  h->pol_set = true;
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_rollout_reset(metrpo_rollout_t* h, const float* states, void* stream_) {
+  if (!h || !states) return set_error(METRPO_ERR_INVALID, "reset: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int rows_pad = h->n_tiles * TILE_M;
+  const int n = std::max(h->cfg.n_envs * h->cfg.state_dim, rows_pad);
+  reset_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(states, h->row_state, h->row_ts, h->row_nreset,
+                                                     h->cfg.n_envs, h->cfg.state_dim, rows_pad);
+  METRPO_CUDA_OK(cudaGetLastError());
+  h->state_set = true;
+  return METRPO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gang schedule: cut the (tile x step) chains into per-slot segment lists of equal total length.
+// A chain is split at most once; the slot that owns the head (t0 == 0, t1 < T) runs it FIRST,
+// the slot that owns the tail runs it LAST and waits on the tile flag (always already set in
+// practice: per >= T).  Heads never wait, so the schedule cannot deadlock.
+// ---------------------------------------------------------------------------------------------
+static int build_schedule(metrpo_rollout* h, int T, std::vector<int4>& segs, int& n_slots) {
+  const int n_tiles = h->n_tiles;
+  n_slots = h->max_slots;
+  const long long total = static_cast<long long>(n_tiles) * T;
+  const long long per = (total + n_slots - 1) / n_slots;
+  segs.assign(static_cast<size_t>(n_slots) * MAX_SEG, make_int4(-1, 0, 0, 0));
+  for (int j = 0; j < n_slots; ++j) {
+    const long long lo = j * per, hi = std::min(total, lo + per);
+    std::vector<int4> head, whole, tail;
+    long long pos = lo;
+    while (pos < hi) {
+      const int tile = static_cast<int>(pos / T), t0 = static_cast<int>(pos % T);
+      const int t1 = static_cast<int>(std::min<long long>(T, t0 + (hi - pos)));
+      int4 sg = make_int4(tile, t0, t1, t0 > 0 ? 1 : 0);
+      if (t0 > 0) tail.push_back(sg);
+      else if (t1 < T) head.push_back(sg);
+      else whole.push_back(sg);
+      pos += t1 - t0;
+    }
+    std::vector<int4> order;
+    order.insert(order.end(), head.begin(), head.end());
+    order.insert(order.end(), whole.begin(), whole.end());
+    order.insert(order.end(), tail.begin(), tail.end());
+    if (order.size() > MAX_SEG) return -1;
+    for (size_t i = 0; i < order.size(); ++i) segs[static_cast<size_t>(j) * MAX_SEG + i] = order[i];
+  }
+  return 0;
+}
+
+static int get_schedule(metrpo_rollout* h, int T, const int4** dev, int* n_slots, cudaStream_t st) {
+  auto it = h->schedules.find(T);
+  if (it != h->schedules.end()) {
+    *dev = it->second;
+    *n_slots = h->schedule_slots[T];
+    return METRPO_OK;
+  }
+  std::vector<int4> segs;
+  int ns = 0;
+  if (build_schedule(h, T, segs, ns) != 0)
+    return set_error(METRPO_ERR_UNSUPPORTED, "run: schedule needs more than %d segments per slot (n_tiles=%d, slots=%d)", MAX_SEG, h->n_tiles, h->max_slots);
+  int4* d = nullptr;
+  METRPO_CUDA_OK(cudaMalloc(&d, segs.size() * sizeof(int4)));
+  // one-time synchronous upload (first call with this horizon only)
+  METRPO_CUDA_OK(cudaMemcpy(d, segs.data(), segs.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  (void)st;
+  h->schedules[T] = d;
+  h->schedule_slots[T] = ns;
+  *dev = d;
+  *n_slots = ns;
+  return METRPO_OK;
+}
+
+static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
+  for (int k = 0; k < h->cfg.n_models; ++k)
+    if (!h->dyn_set[k]) return set_error(METRPO_ERR_STATE, "run: dynamics model %d was never set", k);
+  if (!h->norm_set) return set_error(METRPO_ERR_STATE, "run: normalization constants were never set");
+  const metrpo_rollout_cfg& c = h->cfg;
+  p.S = c.state_dim; p.A = c.action_dim; p.SA = p.S + p.A; p.drop = c.drop_cols; p.Din = h->Din;
+  p.K0 = h->K0; p.H = c.hidden; p.S_pad = h->S_pad; p.K = c.n_models; p.B = c.n_envs;
+  p.T_max = c.max_path_length; p.env_id = c.env_id; p.sam_mode = c.sam_mode;
+  p.NC = h->NC; p.KC = h->KC; p.n_tiles = h->n_tiles;
+  p.wstream = h->wstream; p.model_stride = h->model_stride; p.stage_bytes = h->stage_bytes;
+  p.w0tile_bytes = h->w0tile_bytes; p.w2chunk_bytes = h->w2chunk_bytes; p.off_w2 = h->off_w2;
+  p.off_w0res = h->off_w0res; p.bias = h->bias; p.norm = h->norm; p.pol = h->pol;
+  p.pol_floats = h->pol_floats; p.n_pol_layers = c.n_policy_layers; p.pol_out_tanh = c.policy_out_tanh;
+  p.pol_logstd_off = h->pol_logstd_off;
+  for (int l = 0; l < 4; ++l) p.pl[l] = h->pl[l];
+  p.xbuf = h->xbuf; p.xctr = h->xctr; p.row_state = h->row_state; p.row_ts = h->row_ts;
+  p.row_nreset = h->row_nreset; p.tile_flag = h->tile_flag; p.dbg = h->dbg;
+  p.off_stage = h->off_stage; p.off_sw0res = h->off_sw0res; p.off_z = h->off_z; p.off_h0 = h->off_h0;
+  p.off_h1 = h->off_h1; p.off_sw2 = h->off_sw2; p.off_sbias = h->off_sbias; p.off_snorm = h->off_snorm;
+  p.off_spol = h->off_spol; p.off_bars = h->off_bars;
+  int n_slots = 0;
+  int rc = get_schedule(h, p.n_steps, &p.segs, &n_slots, st);
+  if (rc != METRPO_OK) return rc;
+  p.n_slots = n_slots;
+  METRPO_CUDA_OK(cudaMemsetAsync(h->xctr, 0, h->max_slots * 4, st));
+  METRPO_CUDA_OK(cudaMemsetAsync(h->tile_flag, 0, h->n_tiles * 4, st));
+  METRPO_CUDA_OK(cudaMemsetAsync(h->dbg, 0, h->dbg_words * 4, st));
+  void* args[] = {&p};
+  // cooperative launch: all gang CTAs must be co-resident (they spin on each other)
+  METRPO_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rollout_kernel),
+                                             dim3(n_slots * c.n_models), dim3(NUM_THREADS), args,
+                                             h->smem_bytes, st));
+  h->last_launches = 1;
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_rollout_run(metrpo_rollout_t* h, int n_steps, const float* init_states,
+                                  const float* reset_pool, int R, const float* eps,
+                                  const int32_t* model_idx, const float* std_noise, uint64_t seed,
+                                  uint64_t offset, int determ, float* obs, float* act, float* mean,
+                                  float* rew, uint8_t* done, float* final_states, void* stream_) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "run: null handle");
+  if (n_steps < 1) return set_error(METRPO_ERR_INVALID, "run: n_steps must be >= 1");
+  if (!init_states) return set_error(METRPO_ERR_INVALID, "run: init_states is required");
+  if (!reset_pool || R < 1) return set_error(METRPO_ERR_INVALID, "run: a reset pool with R >= 1 states is required");
+  if (!h->pol_set) return set_error(METRPO_ERR_STATE, "run: policy was never set");
+  METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
+  KParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n_steps = n_steps; p.resume = 0; p.determ = determ ? 1 : 0;
+  p.init_states = init_states; p.reset_pool = reset_pool; p.R = R; p.eps = eps; p.model_idx = model_idx;
+  p.std_noise = std_noise; p.seed = seed; p.offset = offset;
+  p.obs = obs; p.act = act; p.mean = mean; p.rew = rew; p.done = done; p.final_states = final_states;
+  int rc = launch(h, p, static_cast<cudaStream_t>(stream_));
+  if (rc == METRPO_OK) h->state_set = true;
+  return rc;
+}
+
+extern "C" int metrpo_rollout_step(metrpo_rollout_t* h, const float* actions, const int32_t* model_idx,
+                                   const float* std_noise, const float* reset_states, uint64_t seed,
+                                   uint64_t offset, float* obs_out, float* rew_out, uint8_t* done_out,
+                                   void* stream_) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "step: null handle");
+  if (!actions || !reset_states) return set_error(METRPO_ERR_INVALID, "step: actions and reset_states are required");
+  if (!h->state_set) return set_error(METRPO_ERR_STATE, "step: call reset() first");
+  METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
+  KParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n_steps = 1; p.resume = 1; p.determ = 0;
+  p.ext_actions = actions; p.ext_reset_states = reset_states; p.model_idx = model_idx;
+  p.std_noise = std_noise; p.seed = seed; p.offset = offset; p.R = 1;
+  p.rew = rew_out; p.done = done_out; p.final_states = obs_out;
+  return launch(h, p, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int metrpo_rollout_last_launches(const metrpo_rollout_t* h) { return h ? h->last_launches : 0; }
+
+// Synchronise `stream` and report whether the last launch completed: a kernel whose internal
+// waits timed out sets an abort flag and leaves; the message lists which role of which CTA was
+// waiting on which barrier (diagnostics for the mbarrier protocol).
+extern "C" int metrpo_rollout_status(metrpo_rollout_t* h, void* stream_) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "status: null handle");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  METRPO_CUDA_OK(cudaStreamSynchronize(st));
+  std::vector<unsigned> host(h->dbg_words);
+  METRPO_CUDA_OK(cudaMemcpy(host.data(), h->dbg, h->dbg_words * 4, cudaMemcpyDeviceToHost));
+  if (host[0] == 0) return METRPO_OK;
+  char msg[480];
+  int n = snprintf(msg, sizeof(msg), "rollout kernel aborted (wait timeout):");
+  const int warps = NUM_THREADS / 32;
+  int shown = 0;
+  for (int pass = 1; pass <= 2 && shown < 10; ++pass)   // timed-out waits first, then observers
+    for (int b = 0; b < h->max_slots * h->cfg.n_models && shown < 10; ++b)
+      for (int w = 0; w < warps && shown < 10; ++w) {
+        const unsigned* r = &host[DBG_HEADER + (b * warps + w) * DBG_WORDS_PER_WARP];
+        if (r[2] != (unsigned)pass) continue;
+        n += snprintf(msg + n, sizeof(msg) - n, " [cta%d w%d %s bar=%u st=%u g=%u]", b, w,
+                      pass == 1 ? "TIMEOUT" : "saw", r[0], r[1] >> 8, r[1] & 0xff);
+        ++shown;
+      }
+  return set_error(METRPO_ERR_STATE, "%s", msg);
+}

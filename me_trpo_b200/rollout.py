@@ -1,0 +1,174 @@
+"""EnsembleRollout: thin Python owner of a metrpo_rollout_t handle (include/metrpo.h).
+
+Torch owns every tensor; this class only passes raw device pointers + the current stream through
+ctypes.  It is what NeuralNetEnv / VecSimpleEnv / VectorizedSampler (the mirrors of the reference
+sockets) are built on.  No CPU fallback exists: construction fails on a non-sm_100 device.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _lib
+from .envs import ENV_SPECS, canonical_env_name
+
+
+def _f32(t, device):
+    return torch.as_tensor(t, dtype=torch.float32).to(device).contiguous()
+
+
+class EnsembleRollout:
+    """One imaginary vec-env: K dynamics MLPs + Gaussian MLP policy + analytic reward/done for
+    `n_envs` parallel rows (NeuralNetEnv + VecSimpleEnv, env_helpers.py:532-635)."""
+
+    def __init__(self, env, n_models, n_envs, max_path_length, hidden=None, policy_hidden=None,
+                 sam_mode="step_rand", drop_cols=None, policy_out_tanh=False, device=None,
+                 state_dim=None, action_dim=None):
+        name = canonical_env_name(env)
+        spec = ENV_SPECS[name]
+        self.env_name = name
+        self.S = int(state_dim or spec["S"])
+        self.A = int(action_dim or spec["A"])
+        self.drop = int(spec["drop"] if drop_cols is None else drop_cols)
+        self.hidden = int(hidden or spec["hidden"])
+        self.policy_hidden = tuple(policy_hidden if policy_hidden is not None else spec["policy_hidden"])
+        self.K, self.B, self.T_max = int(n_models), int(n_envs), int(max_path_length)
+        self.sam_mode = sam_mode
+        if sam_mode not in _lib.SAM_MODES:
+            raise AssertionError("sam mode %s is not defined." % sam_mode)   # env_helpers.py:634
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("EnsembleRollout needs a CUDA device (sm_100a); there is no CPU path")
+        self._lib = _lib.load()
+        cfg = _lib.RolloutCfg()
+        cfg.state_dim, cfg.action_dim, cfg.drop_cols = self.S, self.A, self.drop
+        cfg.hidden, cfg.n_models, cfg.n_envs = self.hidden, self.K, self.B
+        cfg.max_path_length = self.T_max
+        cfg.env_id = _lib.ENV_IDS[name]
+        cfg.sam_mode = _lib.SAM_MODES[sam_mode]
+        dims = [self.S] + list(self.policy_hidden) + [self.A]
+        if len(dims) - 1 > _lib.MAX_POLICY_LAYERS:
+            raise RuntimeError("policy has too many layers for this build")
+        cfg.n_policy_layers = len(dims) - 1
+        for i, d in enumerate(dims):
+            cfg.policy_dims[i] = d
+        cfg.policy_out_tanh = 1 if policy_out_tanh else 0
+        cfg.precision = 0
+        cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._h = ctypes.c_void_p()
+        _lib.check(self._lib.metrpo_rollout_create(ctypes.byref(cfg), ctypes.byref(self._h)),
+                   "metrpo_rollout_create")
+        self._keep = []          # tensors that must outlive async launches
+        self.log_std = None
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.metrpo_rollout_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parameters -------------------------------------------------------------------------
+    def set_dynamics(self, k, W0, b0, W1, b1, W2, b2):
+        """Weights of model k in the reference's TF layout W[in,out] (training.py:187-208)."""
+        ts = [_f32(t, self.device) for t in (W0, b0, W1, b1, W2, b2)]
+        din = self.S + self.A - self.drop
+        shapes = [(din, self.hidden), (self.hidden,), (self.hidden, self.hidden), (self.hidden,),
+                  (self.hidden, self.S), (self.S,)]
+        for t, s in zip(ts, shapes):
+            if tuple(t.shape) != s:
+                raise ValueError("dynamics weight shape %s, expected %s" % (tuple(t.shape), s))
+        _lib.check(self._lib.metrpo_rollout_set_dynamics(self._h, int(k), *[_lib.ptr(t) for t in ts],
+                                                         _lib.stream_ptr()), "set_dynamics")
+        self._keep.append(ts)
+
+    def set_dynamics_ensemble(self, models):
+        assert len(models) == self.K
+        for k, m in enumerate(models):
+            self.set_dynamics(k, m["W0"], m["b0"], m["W1"], m["b1"], m["W2"], m["b2"])
+
+    def set_normalization(self, in_mean, in_std, diff_mean, diff_std):
+        ts = [_f32(t, self.device) for t in (in_mean, in_std, diff_mean, diff_std)]
+        assert ts[0].numel() == self.S + self.A and ts[2].numel() == self.S
+        _lib.check(self._lib.metrpo_rollout_set_normalization(self._h, *[_lib.ptr(t) for t in ts],
+                                                              _lib.stream_ptr()), "set_normalization")
+        self._keep.append(ts)
+
+    def set_policy(self, Ws, bs, log_std):
+        n = len(self.policy_hidden) + 1
+        assert len(Ws) == n and len(bs) == n
+        Ws = [_f32(w, self.device) for w in Ws]
+        bs = [_f32(b, self.device) for b in bs]
+        ls = _f32(log_std, self.device)
+        Wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in Ws])
+        bp = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bs])
+        _lib.check(self._lib.metrpo_rollout_set_policy(self._h, Wp, bp, _lib.ptr(ls), _lib.stream_ptr()),
+                   "set_policy")
+        self._keep.append((Ws, bs, ls))
+        self.log_std = ls
+
+    # -- B1: step-granular vec env ------------------------------------------------------------
+    def reset(self, states):
+        st = _f32(states, self.device)
+        assert tuple(st.shape) == (self.B, self.S)
+        _lib.check(self._lib.metrpo_rollout_reset(self._h, _lib.ptr(st), _lib.stream_ptr()), "reset")
+        self._keep.append(st)
+
+    def step(self, actions, reset_states, model_idx=None, std_noise=None, seed=0, offset=0):
+        dev = self.device
+        act = _f32(actions, dev)
+        rs = _f32(reset_states, dev)
+        mi = None if model_idx is None else torch.as_tensor(model_idx, dtype=torch.int32).to(dev).contiguous()
+        sn = None if std_noise is None else _f32(std_noise, dev)
+        obs = torch.empty(self.B, self.S, device=dev)
+        rew = torch.empty(self.B, device=dev)
+        done = torch.empty(self.B, dtype=torch.uint8, device=dev)
+        _lib.check(self._lib.metrpo_rollout_step(self._h, _lib.ptr(act), _lib.ptr(mi), _lib.ptr(sn),
+                                                 _lib.ptr(rs), int(seed), int(offset), _lib.ptr(obs),
+                                                 _lib.ptr(rew), _lib.ptr(done), _lib.stream_ptr()), "step")
+        self._keep = self._keep[-8:] + [(act, rs, mi, sn)]
+        return obs, rew, done
+
+    # -- B2: whole-horizon fused rollout ------------------------------------------------------
+    def run(self, n_steps, init_states, reset_pool, eps=None, model_idx=None, std_noise=None, seed=0,
+            offset=0, determ=False, out=None, want=("obs", "act", "mean", "rew", "done")):
+        """Returns dict of time-major device tensors obs[T,B,S], act[T,B,A] (unclipped), mean[T,B,A],
+        rew[T,B], done[T,B] (uint8) and final_states[B,S]."""
+        dev, T, B, S, A = self.device, int(n_steps), self.B, self.S, self.A
+        init = _f32(init_states, dev)
+        pool = _f32(reset_pool, dev)
+        assert tuple(init.shape) == (B, S) and pool.dim() == 2 and pool.shape[1] == S
+        ep = None if eps is None else _f32(eps, dev)
+        mi = None if model_idx is None else torch.as_tensor(model_idx, dtype=torch.int32).to(dev).contiguous()
+        sn = None if std_noise is None else _f32(std_noise, dev)
+        if ep is not None:
+            assert tuple(ep.shape) == (T, B, A)
+        if mi is not None:
+            assert tuple(mi.shape) == (T, B)
+        if out is None:
+            out = {}
+        shapes = dict(obs=(T, B, S), act=(T, B, A), mean=(T, B, A), rew=(T, B), done=(T, B))
+        for name in want:
+            if name not in out:
+                dt = torch.uint8 if name == "done" else torch.float32
+                out[name] = torch.empty(shapes[name], dtype=dt, device=dev)
+        if "final_states" not in out:
+            out["final_states"] = torch.empty(B, S, device=dev)
+        g = lambda n: _lib.ptr(out.get(n)) if n in want else None
+        _lib.check(self._lib.metrpo_rollout_run(
+            self._h, T, _lib.ptr(init), _lib.ptr(pool), int(pool.shape[0]), _lib.ptr(ep), _lib.ptr(mi),
+            _lib.ptr(sn), int(seed), int(offset), 1 if determ else 0, g("obs"), g("act"), g("mean"),
+            g("rew"), g("done"), _lib.ptr(out["final_states"]), _lib.stream_ptr()), "run")
+        self._keep = self._keep[-8:] + [(init, pool, ep, mi, sn)]
+        return out
+
+    def synchronize(self):
+        """Wait for the stream and raise if the last kernel aborted on an internal wait timeout."""
+        _lib.check(self._lib.metrpo_rollout_status(self._h, _lib.stream_ptr()), "rollout kernel")
+
+    def last_launches(self):
+        return int(self._lib.metrpo_rollout_last_launches(self._h))
