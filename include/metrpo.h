@@ -152,6 +152,11 @@ int metrpo_rollout_run(metrpo_rollout_t* h, int n_steps, const float* init_state
  * aborts itself instead of hanging the GPU). */
 int metrpo_rollout_status(metrpo_rollout_t* h, void* stream);
 
+/* Dev tools: event trace of one CTA (clock64 stamps of its producer / MMA / epilogue roles) for
+ * its local steps [t0,t1); out_host receives 3 x 4096 uint64 (code << 40 | clock). */
+int metrpo_rollout_set_trace(metrpo_rollout_t* h, int cta, int t0, int t1);
+int metrpo_rollout_get_trace(metrpo_rollout_t* h, unsigned long long* out_host);
+
 /* number of kernels the last run()/step() call launched on the stream (bench gpu_launches) */
 int metrpo_rollout_last_launches(const metrpo_rollout_t* h);
 

@@ -105,6 +105,8 @@ struct metrpo_rollout {
   int* row_nreset = nullptr;
   unsigned* tile_flag = nullptr;
   unsigned* dbg = nullptr;
+  unsigned long long* trace = nullptr;
+  int trace_cta = 0, trace_t0 = 0, trace_t1 = 0;
   int dbg_words = 0;
   std::map<int, int4*> schedules;   // n_steps -> device [max_slots][MAX_SEG]
   std::map<int, int> schedule_slots;
@@ -125,7 +127,7 @@ static void free_handle(metrpo_rollout* h) {
   if (!h) return;
   cudaFree(h->wstream); cudaFree(h->bias); cudaFree(h->norm); cudaFree(h->pol); cudaFree(h->xbuf);
   cudaFree(h->xctr); cudaFree(h->row_state); cudaFree(h->row_ts); cudaFree(h->row_nreset);
-  cudaFree(h->tile_flag); cudaFree(h->dbg);
+  cudaFree(h->tile_flag); cudaFree(h->dbg); cudaFree(h->trace);
   for (auto& kv : h->schedules) cudaFree(kv.second);
   delete h;
 }
@@ -398,6 +400,7 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
   for (int l = 0; l < 4; ++l) p.pl[l] = h->pl[l];
   p.xbuf = h->xbuf; p.xctr = h->xctr; p.row_state = h->row_state; p.row_ts = h->row_ts;
   p.row_nreset = h->row_nreset; p.tile_flag = h->tile_flag; p.dbg = h->dbg;
+  p.trace = h->trace; p.trace_cta = h->trace_cta; p.trace_t0 = h->trace_t0; p.trace_t1 = h->trace_t1;
   p.off_stage = h->off_stage; p.off_sw0res = h->off_sw0res; p.off_z = h->off_z; p.off_h0 = h->off_h0;
   p.off_h1 = h->off_h1; p.off_sw2 = h->off_sw2; p.off_sbias = h->off_sbias; p.off_snorm = h->off_snorm;
   p.off_spol = h->off_spol; p.off_bars = h->off_bars;
@@ -482,4 +485,23 @@ extern "C" int metrpo_rollout_status(metrpo_rollout_t* h, void* stream_) {
         ++shown;
       }
   return set_error(METRPO_ERR_STATE, "%s", msg);
+}
+
+// Dev tool: record an event trace (role-private logs of code<<40 | clock64) of CTA `cta` for its
+// local steps [t0, t1).  out (host, 3*4096 u64) receives the logs after a synchronising
+// metrpo_rollout_get_trace.
+extern "C" int metrpo_rollout_set_trace(metrpo_rollout_t* h, int cta, int t0, int t1) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "set_trace: null handle");
+  if (!h->trace) {
+    METRPO_CUDA_OK(cudaMalloc(&h->trace, 3 * TRACE_CAP * 8));
+  }
+  METRPO_CUDA_OK(cudaMemset(h->trace, 0, 3 * TRACE_CAP * 8));
+  h->trace_cta = cta; h->trace_t0 = t0; h->trace_t1 = t1;
+  return METRPO_OK;
+}
+extern "C" int metrpo_rollout_get_trace(metrpo_rollout_t* h, unsigned long long* out_host) {
+  if (!h || !h->trace || !out_host) return set_error(METRPO_ERR_INVALID, "get_trace: no trace");
+  METRPO_CUDA_OK(cudaDeviceSynchronize());
+  METRPO_CUDA_OK(cudaMemcpy(out_host, h->trace, 3 * TRACE_CAP * 8, cudaMemcpyDeviceToHost));
+  return METRPO_OK;
 }

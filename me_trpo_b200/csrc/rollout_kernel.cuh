@@ -114,6 +114,8 @@ struct KParams {
   int* row_ts;            // [n_tiles*128]
   int* row_nreset;        // [n_tiles*128]
   unsigned* tile_flag;    // [n_tiles]
+  unsigned long long* trace;   // optional event trace of one CTA (dev tool), or nullptr
+  int trace_cta, trace_t0, trace_t1;
   unsigned* dbg;          // [DBG_HEADER + grid*6*4] abort flag + wait records
   const int4* segs;       // [n_slots][MAX_SEG] = (tile, t0, t1, wait_flag); tile < 0 -> unused
   // smem carve-up (byte offsets from the 1024-aligned base)
@@ -188,6 +190,16 @@ __device__ __forceinline__ bool wait_ge(const unsigned* ptr, unsigned target, un
 }
 #define WAITB(idx, par, info) \
   do { if (!wait_bar(&bars[idx], (par), p.dbg, (idx), (info))) goto bail; } while (0)
+
+// optional event trace (dev tool): role-private logs of (code << 40 | clock) for one CTA and a
+// window of steps; enabled by metrpo_rollout_set_trace.  role 0 producer, 1 MMA, 2 epilogue.
+constexpr int TRACE_CAP = 4096;
+#define TRACE(role, code)                                                                    \
+  do {                                                                                       \
+    if (tr_on && tr_n < TRACE_CAP)                                                           \
+      p.trace[(role) * TRACE_CAP + tr_n++] =                                                 \
+          (static_cast<unsigned long long>(code) << 40) | (clock64() & 0xFFFFFFFFFFull);     \
+  } while (0)
 
 // per-row analytic cost (reward = -cost); u is the clipped action.  envs/com_*_env.py
 __device__ __forceinline__ float env_cost(int env_id, int S, int A, const float (&xn)[SMAX],
@@ -303,6 +315,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
 
   // ---- one-time setup ----
   int st_dbg = 0;   // progress counter reported by the wait diagnostics
+  bool tr_on = false;
+  int tr_n = 0;
   if (tid == 0) {
     abort_smem = 0;
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
@@ -343,8 +357,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           for (int nc = 0; nc < p.NC; ++nc) {
             for (int kc = 0; kc < p.KC; ++kc) {
               st_dbg = (st << 8) | (nc * p.KC + kc);
+              tr_on = p.trace && blockIdx.x == p.trace_cta && st >= p.trace_t0 && st < p.trace_t1;
               const uint32_t s = gs % NSTAGE, n = gs / NSTAGE;
+              TRACE(0, 0x100 | (nc * p.KC + kc));
               WAITB(B_EMPTY + s, (n & 1) ^ 1, (uint32_t)st_dbg);
+              TRACE(0, 0x200 | (nc * p.KC + kc));
               mbar_arrive_expect_tx(&bars[B_FULL + s], p.stage_bytes);
               bulk_g2s_hint(sStage + s * p.stage_bytes,
                             wm + static_cast<size_t>(nc * p.KC + kc) * p.stage_bytes, p.stage_bytes,
@@ -390,7 +407,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
         uint32_t gs = 0, gc = 0, hs = 0, zn = 0, a1f = 0, w2n = 0;
         WAITB(B_W0RES, 0, (uint32_t)st_dbg);
         for (int st = 0; st < total_steps; ++st) {
+          tr_on = p.trace && blockIdx.x == p.trace_cta && st >= p.trace_t0 && st < p.trace_t1;
+          TRACE(1, 0x1000);
           WAITB(B_ZREADY, zn & 1, (uint32_t)st_dbg); ++zn;
+          TRACE(1, 0x1001);
           tc_fence_after();
           // prologue: L0 of chunks 0 and 1 from the resident W0 tiles
           for (int c = 0; c < 2 && c < NCH; ++c) {
@@ -405,8 +425,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               const int g = nc * p.KC + kc;
               st_dbg = (st << 8) | g;
               const uint32_t b = gc & 1, s = gs % NSTAGE;
+              TRACE(1, 0x100 | g);
               WAITB(B_FULL + s, (gs / NSTAGE) & 1, (uint32_t)st_dbg);
+              TRACE(1, 0x200 | g);
               WAITB(B_H0FULL + b, (gc >> 1) & 1, (uint32_t)st_dbg);
+              TRACE(1, 0x300 | g);
               tc_fence_after();
               if (g + 2 < NCH) {   // L0 of chunk g+2 (its W0 tile rides in this stage)
                 for (int j = 0; j < k0steps; ++j)
@@ -428,6 +451,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               umma_commit(&bars[B_EMPTY + s]);
               umma_commit(&bars[B_H0FREE + b]);
               if (kc == p.KC - 1) umma_commit(&bars[B_ACC1FULL]);
+              TRACE(1, 0x400 | g);
               ++gs; ++gc;
             }
             // L2 of pass nc: acc2 += relu(h1 chunk) * W2 chunk
@@ -446,6 +470,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
             umma_commit(&bars[B_W2EMPTY]);
           }
           umma_commit(&bars[B_ACC2FULL]);
+          TRACE(1, 0x1002);
         }
       }
     } else {
@@ -497,6 +522,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
         }
 
         for (int t = t0; t < t1; ++t) {
+          tr_on = p.trace && blockIdx.x == p.trace_cta && e == 0 && (t - t0) >= p.trace_t0 && (t - t0) < p.trace_t1;
+          TRACE(2, 0x1000);
           // ================= begin step: action + Z operand =================
           if (p.ext_actions != nullptr) {
 #pragma unroll
@@ -583,6 +610,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(&bars[B_ZREADY]);
+          TRACE(2, 0x1001);
 
           // ================= per-chunk epilogues =================
           for (int g = 0; g < NCH; ++g) {
@@ -590,16 +618,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
             {
               const uint32_t b = gc & 1;
               uint32_t v0[32], v1[32];
+              TRACE(2, 0x100 | g);
               WAITB(B_ACC0FULL + b, (gc >> 1) & 1, (uint32_t)st_dbg);
+              TRACE(2, 0x200 | g);
               tc_fence_after();
               tmem_ld32(tmem + lane_base + TM_ACC0 + b * 64, v0);
               tmem_ld32(tmem + lane_base + TM_ACC0 + b * 64 + 32, v1);
               tmem_ld_wait();
+              TRACE(2, 0x300 | g);
               WAITB(B_H0FREE + b, ((gc >> 1) & 1) ^ 1, (uint32_t)st_dbg);
+              TRACE(2, 0x400 | g);
               relu_pack_store(v0, v1, sB0 + (g % p.KC) * 64, sH0 + b * H_TILE_BYTES, r);
+              TRACE(2, 0x500 | g);
               fence_proxy_async_smem();
               tc_fence_before();
               mbar_arrive(&bars[B_H0FULL + b]);
+              TRACE(2, 0x600 | g);
               ++gc;
             }
             // layer-1 pass epilogue.  Pass nc is drained after the first two chunks of pass nc+1
@@ -609,7 +643,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
             if (g == NCH - 1) drain_nc = p.NC - 1;
             else if (g >= p.KC && (g % p.KC) == 1) drain_nc = g / p.KC - 1;
             if (drain_nc >= 0) {
+              TRACE(2, 0x700 | g);
               WAITB(B_ACC1FULL, a1n & 1, (uint32_t)st_dbg); ++a1n;
+              TRACE(2, 0x800 | g);
               tc_fence_after();
               for (int sub = 0; sub < 4; ++sub) {
                 uint32_t v0[32], v1[32];
@@ -624,6 +660,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                 mbar_arrive(&bars[B_H1FULL + bb]);
                 ++hs;
               }
+              TRACE(2, 0x900 | g);
             }
           }
 
@@ -631,7 +668,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           float cand[SMAX];
           {
             uint32_t v[32];
+            TRACE(2, 0x1002);
             WAITB(B_ACC2FULL, a2n & 1, (uint32_t)st_dbg); ++a2n;
+            TRACE(2, 0x1003);
             tc_fence_after();
             tmem_ld32(tmem + lane_base + TM_ACC2, v);
             tmem_ld_wait();
@@ -662,6 +701,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
             }
             named_bar_sync(1, EPI_THREADS);
             if (*reinterpret_cast<volatile int*>(&abort_smem)) goto bail;
+            TRACE(2, 0x1004);
             ++xn_cnt;
             if (mode == METRPO_SAM_STEP_RAND || mode == METRPO_SAM_EPS_RAND ||
                 mode == METRPO_SAM_ONE_MODEL) {
@@ -750,6 +790,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
             if (p.rew) p.rew[o] = reward;
             if (p.done) p.done[o] = dn ? 1 : 0;
           }
+          TRACE(2, 0x1005);
 #pragma unroll
           for (int s = 0; s < SMAX; ++s) x[s] = xnext[s];
           if (dn) {   // env_helpers.py:605-606 -> reset(dones)

@@ -51,6 +51,8 @@ _PROTOS = {
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "metrpo_rollout_last_launches": (_i, [_vp]),
     "metrpo_rollout_status": (_i, [_vp, _vp]),
+    "metrpo_rollout_set_trace": (_i, [_vp, _i, _i, _i]),
+    "metrpo_rollout_get_trace": (_i, [_vp, _vp]),
     "metrpo_selftest_umma": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 
