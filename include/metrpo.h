@@ -167,6 +167,12 @@ int metrpo_rollout_last_launches(const metrpo_rollout_t* h);
 int metrpo_selftest_umma(int mode, int N, int K, int reps, const void* A_bf16, const void* B_bf16,
                          float* C, unsigned long long* cycles, void* stream);
 
+/* Dev tool: tensor-pipe micro-benchmark.  Issues reps x 4 tcgen05.mma (M=128, K=16, given N) from
+ * a warp-uniform loop; out_dev[0] = clock64 span of the issue loop, out_dev[1] = span until the
+ * final commit is observed.  ts_mode 1: A operand from TMEM, 0: from shared memory. */
+int metrpo_bench_mma(int ts_mode, int N, int reps, int two_acc, int a_col, int d_col,
+                     int wait_each, unsigned long long* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,9 +29,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n0, float& n1) {
   float u1 = (static_cast<float>(xa >> 8) + 1.0f) * 5.9604644775390625e-08f;  // (0,1]
   float u2 = static_cast<float>(xb >> 8) * 5.9604644775390625e-08f;           // [0,1)
-  float r = sqrtf(-2.0f * logf(u1));
+  float r = sqrtf(-2.0f * __logf(u1));
   float s, c;
-  sincosf(6.283185307179586f * u2, &s, &c);
+  sincospif(2.0f * u2, &s, &c);   // exact argument reduction for [0, 2): cheap and accurate
   n0 = r * c;
   n1 = r * s;
 }

@@ -13,7 +13,7 @@ namespace metrpo {
 // ---------------------------------------------------------------------------------------------
 // packing kernels (one thread per destination element)
 // ---------------------------------------------------------------------------------------------
-// stage (nc,kc) = [ W1 tile: n in [256nc,+256) x k in [64kc,+64), SW128 | W0 tile (kc+2)%KC ]
+// stage (nc,kc) = W1 tile: n in [256nc,+256) x k in [64kc,+64), SW128 K-major
 __global__ void pack_w1_kernel(const float* __restrict__ W1, uint8_t* __restrict__ dst, int H,
                                int KC, uint32_t stage_bytes) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -23,23 +23,21 @@ __global__ void pack_w1_kernel(const float* __restrict__ W1, uint8_t* __restrict
   uint8_t* st = dst + static_cast<size_t>(nc * KC + kc) * stage_bytes;
   *reinterpret_cast<__nv_bfloat16*>(st + sw128_off(nl, kl)) = __float2bfloat16_rn(W1[i]);
 }
-// W0 tile j: n in [64j,+64) x k in [0,K0), no-swizzle core-matrix layout, zero padded k >= Din
-__global__ void pack_w0_kernel(const float* __restrict__ W0, uint8_t* __restrict__ dst, int H,
-                               int Din, int K0, int NC, int KC, uint32_t stage_bytes,
-                               uint32_t w0tile_bytes, uint32_t off_w0res) {
+// W0 group tile j: n in [128j,+128) x k in [0,K0), no-swizzle core-matrix layout, zero padded.
+// rows Din / Din+1 hold the bf16 hi / lo parts of b0 (Z carries 1.0 in those two columns)
+__global__ void pack_w0_kernel(const float* __restrict__ W0, const float* __restrict__ b0,
+                               uint8_t* __restrict__ dst, int H, int Din, int K0,
+                               uint32_t w0g_bytes, uint32_t off_w0g) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K0 * H) return;
   const int kk = i / H, n = i % H;
-  const int j = n / 64, nl = n % 64;
-  const __nv_bfloat16 v = __float2bfloat16_rn(kk < Din ? W0[kk * H + n] : 0.f);
-  const uint32_t off = noswz_off(nl, kk, 64);
-  // tile j rides in the stage whose kc satisfies (kc + 2) % KC == j, in every nc pass
-  const int kc = (j + KC - 2) % KC;
-  for (int nc = 0; nc < NC; ++nc) {
-    uint8_t* st = dst + static_cast<size_t>(nc * KC + kc) * stage_bytes + W1_TILE_BYTES;
-    *reinterpret_cast<__nv_bfloat16*>(st + off) = v;
-  }
-  if (j < 2) *reinterpret_cast<__nv_bfloat16*>(dst + off_w0res + j * w0tile_bytes + off) = v;
+  const int j = n / 128, nl = n % 128;
+  float val = 0.f;
+  if (kk < Din) val = W0[kk * H + n];
+  else if (kk == Din) val = __bfloat162float(__float2bfloat16_rn(b0[n]));
+  else if (kk == Din + 1) val = b0[n] - __bfloat162float(__float2bfloat16_rn(b0[n]));
+  *reinterpret_cast<__nv_bfloat16*>(dst + off_w0g + static_cast<size_t>(j) * w0g_bytes +
+                                    noswz_off(nl, kk, 128)) = __float2bfloat16_rn(val);
 }
 // W2 chunk nc: 4 sub-tiles [S_pad rows (s)][64 k] SW128, zero padded s >= S
 __global__ void pack_w2_kernel(const float* __restrict__ W2, uint8_t* __restrict__ dst, int H, int S,
@@ -91,7 +89,7 @@ using namespace metrpo;
 struct metrpo_rollout {
   metrpo_rollout_cfg cfg;
   int Din, K0, S_pad, NC, KC, n_tiles, max_slots, num_sms;
-  uint32_t stage_bytes, w0tile_bytes, w2chunk_bytes, off_w2, off_w0res;
+  uint32_t stage_bytes, w0g_bytes, w2chunk_bytes, off_w2, off_w0g;
   size_t model_stride;
   // device buffers
   uint8_t* wstream = nullptr;
@@ -114,8 +112,8 @@ struct metrpo_rollout {
   PolicyLayer pl[4];
   int pol_floats = 0, pol_logstd_off = 0;
   // smem layout
-  uint32_t off_stage, off_sw0res, off_z, off_h0, off_h1, off_sw2, off_sbias, off_snorm, off_spol,
-      off_bars, smem_bytes;
+  uint32_t off_stage, off_sw0g, off_scr, off_sw2, off_sbias, off_snorm, off_spol, off_bars,
+      smem_bytes;
   std::vector<char> dyn_set;
   bool norm_set = false, pol_set = false, state_set = false;
   int last_launches = 0;
@@ -174,18 +172,18 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   h->cfg = c;
   h->num_sms = prop.multiProcessorCount;
   h->Din = c.state_dim + c.action_dim - c.drop_cols;
-  h->K0 = static_cast<int>(align_up(h->Din, 16));
+  h->K0 = static_cast<int>(align_up(h->Din + 2, 16));   // +2: ones columns carrying b0 (hi, lo)
   h->S_pad = static_cast<int>(align_up(c.state_dim, 16));
   h->NC = c.hidden / 256;
   h->KC = c.hidden / 64;
   h->n_tiles = (c.n_envs + TILE_M - 1) / TILE_M;
   h->max_slots = std::min(h->n_tiles, h->num_sms / c.n_models);
-  h->w0tile_bytes = 64 * h->K0 * 2;
-  h->stage_bytes = W1_TILE_BYTES + h->w0tile_bytes;
+  h->w0g_bytes = 128 * h->K0 * 2;
+  h->stage_bytes = W1_TILE_BYTES;
   h->w2chunk_bytes = h->S_pad * 256 * 2;
   h->off_w2 = h->NC * h->KC * h->stage_bytes;
-  h->off_w0res = h->off_w2 + h->NC * h->w2chunk_bytes;
-  h->model_stride = align_up(h->off_w0res + 2 * h->w0tile_bytes, 1024);
+  h->off_w0g = h->off_w2 + h->NC * h->w2chunk_bytes;
+  h->model_stride = align_up(h->off_w0g + (c.hidden / 128) * h->w0g_bytes, 1024);
   h->dyn_set.assign(c.n_models, 0);
 
   // policy blob layout
@@ -201,14 +199,12 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   h->pol_logstd_off = off; off += AMAX;
   h->pol_floats = off;
 
-  // shared-memory carve-up
+  // shared-memory carve-up (A operands live in TMEM; smem holds the weight ring + constants)
   uint32_t o = 0;
   h->off_stage = o; o += NSTAGE * h->stage_bytes;
-  h->off_sw0res = o; o += 2 * h->w0tile_bytes;
-  h->off_z = o; o += TILE_M * h->K0 * 2;
-  o = align_up(o, 1024); h->off_h0 = o; o += 2 * H_TILE_BYTES;
-  h->off_h1 = o; o += 2 * H_TILE_BYTES;
-  h->off_sw2 = o; o += h->w2chunk_bytes;
+  h->off_sw0g = o; o += 2 * h->w0g_bytes;
+  o = align_up(o, 1024); h->off_sw2 = o; o += h->w2chunk_bytes;
+  h->off_scr = o; o += std::max(c.state_dim + c.action_dim, HPMAX) * TILE_M * 4;
   h->off_sbias = o; o += (2 * c.hidden + 32) * 4;
   h->off_snorm = o; o += align_up((2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4, 16);
   h->off_spol = o; o += align_up(h->pol_floats * 4, 16);
@@ -219,9 +215,9 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     delete h;
     return set_error(METRPO_ERR_UNSUPPORTED, "create: config needs %d B of shared memory per CTA (limit %d)", need, (int)prop.sharedMemPerBlockOptin);
   }
-  if ((c.state_dim + c.action_dim) * TILE_M * 4 > 2 * H_TILE_BYTES) {
+  if (h->K0 > 64) {
     delete h;
-    return set_error(METRPO_ERR_UNSUPPORTED, "create: S + A too large for the scratch tiles");
+    return set_error(METRPO_ERR_UNSUPPORTED, "create: padded dynamics input %d > 64 (TMEM budget of the Z operand)", h->K0);
   }
 
   const size_t rows_pad = static_cast<size_t>(h->n_tiles) * TILE_M;
@@ -271,8 +267,8 @@ extern "C" int metrpo_rollout_set_dynamics(metrpo_rollout_t* h, int k, const flo
   uint8_t* dst = h->wstream + static_cast<size_t>(k) * h->model_stride;
   const int T = 256;
   pack_w1_kernel<<<(static_cast<size_t>(H) * H + T - 1) / T, T, 0, st>>>(W1, dst, H, h->KC, h->stage_bytes);
-  pack_w0_kernel<<<(h->K0 * H + T - 1) / T, T, 0, st>>>(W0, dst, H, h->Din, h->K0, h->NC, h->KC,
-                                                        h->stage_bytes, h->w0tile_bytes, h->off_w0res);
+  pack_w0_kernel<<<(h->K0 * H + T - 1) / T, T, 0, st>>>(W0, b0, dst, H, h->Din, h->K0, h->w0g_bytes,
+                                                        h->off_w0g);
   pack_w2_kernel<<<(H * h->S_pad + T - 1) / T, T, 0, st>>>(W2, dst, H, S, h->S_pad, h->off_w2, h->w2chunk_bytes);
   pack_bias_kernel<<<(2 * H + 32 + T - 1) / T, T, 0, st>>>(b0, b1, b2, h->bias + static_cast<size_t>(k) * (2 * H + 32), H, S);
   METRPO_CUDA_OK(cudaGetLastError());
@@ -393,16 +389,16 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
   p.T_max = c.max_path_length; p.env_id = c.env_id; p.sam_mode = c.sam_mode;
   p.NC = h->NC; p.KC = h->KC; p.n_tiles = h->n_tiles;
   p.wstream = h->wstream; p.model_stride = h->model_stride; p.stage_bytes = h->stage_bytes;
-  p.w0tile_bytes = h->w0tile_bytes; p.w2chunk_bytes = h->w2chunk_bytes; p.off_w2 = h->off_w2;
-  p.off_w0res = h->off_w0res; p.bias = h->bias; p.norm = h->norm; p.pol = h->pol;
+  p.w0g_bytes = h->w0g_bytes; p.w2chunk_bytes = h->w2chunk_bytes; p.off_w2 = h->off_w2;
+  p.off_w0g = h->off_w0g; p.bias = h->bias; p.norm = h->norm; p.pol = h->pol;
   p.pol_floats = h->pol_floats; p.n_pol_layers = c.n_policy_layers; p.pol_out_tanh = c.policy_out_tanh;
   p.pol_logstd_off = h->pol_logstd_off;
   for (int l = 0; l < 4; ++l) p.pl[l] = h->pl[l];
   p.xbuf = h->xbuf; p.xctr = h->xctr; p.row_state = h->row_state; p.row_ts = h->row_ts;
   p.row_nreset = h->row_nreset; p.tile_flag = h->tile_flag; p.dbg = h->dbg;
   p.trace = h->trace; p.trace_cta = h->trace_cta; p.trace_t0 = h->trace_t0; p.trace_t1 = h->trace_t1;
-  p.off_stage = h->off_stage; p.off_sw0res = h->off_sw0res; p.off_z = h->off_z; p.off_h0 = h->off_h0;
-  p.off_h1 = h->off_h1; p.off_sw2 = h->off_sw2; p.off_sbias = h->off_sbias; p.off_snorm = h->off_snorm;
+  p.off_stage = h->off_stage; p.off_sw0g = h->off_sw0g; p.off_scr = h->off_scr;
+  p.off_sw2 = h->off_sw2; p.off_sbias = h->off_sbias; p.off_snorm = h->off_snorm;
   p.off_spol = h->off_spol; p.off_bars = h->off_bars;
   int n_slots = 0;
   int rc = get_schedule(h, p.n_steps, &p.segs, &n_slots, st);
@@ -492,6 +488,9 @@ extern "C" int metrpo_rollout_status(metrpo_rollout_t* h, void* stream_) {
 // metrpo_rollout_get_trace.
 extern "C" int metrpo_rollout_set_trace(metrpo_rollout_t* h, int cta, int t0, int t1) {
   if (!h) return set_error(METRPO_ERR_INVALID, "set_trace: null handle");
+#ifndef METRPO_TRACE
+  return set_error(METRPO_ERR_UNSUPPORTED, "set_trace: library was built without -DMETRPO_TRACE");
+#endif
   if (!h->trace) {
     METRPO_CUDA_OK(cudaMalloc(&h->trace, 3 * TRACE_CAP * 8));
   }

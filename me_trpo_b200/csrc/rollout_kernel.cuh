@@ -20,20 +20,28 @@
 //
 // Inside a CTA (192 threads):
 //   warp 0    producer: streams the model's pre-packed bf16 weight tiles L2 -> smem with
-//             cp.async.bulk (TMA engine) through a 3-stage mbarrier ring
-//   warp 1    MMA issuer: one thread issues tcgen05.mma (M=128, fp32 accumulators in TMEM)
-//   warps 2-5 epilogue/compute: TMEM -> registers -> bias+ReLU -> bf16 -> smem operand tiles,
-//             plus the per-step serial section (residual/de-normalise, exchange, select,
-//             reward/done/reset, trajectory write, policy MLP, normalise -> Z operand tile)
+//             cp.async.bulk (TMA engine) through a 4-stage mbarrier ring
+//   warp 1    MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma (M=128, fp32
+//             accumulators in TMEM); lanes 0/1 probe the next chunk's mbarriers while the
+//             current chunk's MMAs are queued
+//   warps 2-5 epilogue/compute: TMEM -> registers -> (bias)+ReLU -> bf16 -> back to TMEM as the
+//             next layer's A operand, plus the per-step serial section (residual/de-normalise,
+//             exchange, select, reward/done/reset, trajectory write, policy MLP, normalise -> Z)
 //
 // Per step and model the MLP  z[128,K0] -> H -> H -> S  is evaluated as
 //   for nc in H/256 output chunks of layer 1:          (acc1: 256 TMEM columns)
 //     for kc in H/64 reduction chunks:
-//        L0: acc0[b] = Z * W0[:, 64-chunk kc]           (N=64, K=K0; recomputed per nc pass because
-//                                                         128 x H activations do not fit on an SM)
-//        epilogue: H0[b] = bf16(relu(acc0[b] + b0))     (SW128 K-major A operand, 16 KB)
-//        L1: acc1 += H0[b] * W1[kc chunk, nc chunk]     (N=256, K=64: 4 MMAs)
-//     epilogue: 4 x (H1[bb] = bf16(relu(acc1[:,64 cols] + b1)));  L2: acc2 += H1[bb] * W2 chunk
+//        L0 (every 2nd chunk): acc0 = Z(tmem) * W0[:, 128 columns]   (N=128, K=K0; recomputed per
+//                                                         nc pass because 128 x H activations do
+//                                                         not fit on an SM; b0 rides in two
+//                                                         constant-1 columns of Z.  Every MMA at
+//                                                         M=128 costs >= 128 cycles whatever N,
+//                                                         hence the widest N that fits TMEM)
+//        epilogue: H0[b] = bf16(relu(acc0[64 cols]))    (tcgen05.st back to TMEM: the A operand
+//                                                         of L1 never touches shared memory)
+//        L1: acc1 += H0[b](tmem) * W1[kc chunk, nc chunk]   (N=256, K=64: 4 MMAs, B from smem)
+//     epilogue: 4 x 64 columns of acc1 -> bf16(relu(. + b1)) written IN PLACE into acc1's own
+//               columns; L2: acc2 += H1(tmem) * W2 chunk   (N=S_pad, K=256: 16 MMAs)
 //   next_state = (diff_mean + diff_std * (acc2 + b2)) + x          (training.py:257)
 #pragma once
 #include "umma.cuh"
@@ -42,37 +50,38 @@
 namespace metrpo {
 
 constexpr int TILE_M = 128;
-constexpr int NSTAGE = 3;
-constexpr int SMAX = 32;      // max state dim held in registers (v1)
-constexpr int AMAX = 8;       // max action dim (v1)
-constexpr int HPMAX = 32;     // max policy hidden width (v1)
+constexpr int NSTAGE = 4;
+constexpr int SMAX = 32;      // max state dim held in registers
+constexpr int AMAX = 8;       // max action dim
+constexpr int HPMAX = 32;     // max policy hidden width
 constexpr int MAX_SEG = 32;   // segments per gang slot
 constexpr int W1_TILE_BYTES = 256 * 64 * 2;   // 32 KB: [256 n][64 k] bf16, SW128
-constexpr int H_TILE_BYTES = 128 * 64 * 2;    // 16 KB: [128 rows][64 k] bf16, SW128
 constexpr int NUM_THREADS = 192;
 constexpr int EPI_THREADS = 128;
 
 // TMEM column map (512 allocated)
-constexpr uint32_t TM_ACC1 = 0;      // 256 cols
-constexpr uint32_t TM_ACC0 = 256;    // 2 x 64 cols
+constexpr uint32_t TM_ACC1 = 0;      // 256 cols fp32; after the drain: 4 x 32 cols of packed bf16 H1
+constexpr uint32_t TM_ACC0 = 256;    // 128 cols: layer-0 accumulator of one group (2 chunks)
 constexpr uint32_t TM_ACC2 = 384;    // S_pad (<= 32) cols
+constexpr uint32_t TM_H0 = 416;      // 2 x 32 cols: relu(h0) chunk as packed bf16 pairs (A of L1)
+constexpr uint32_t TM_Z = 480;       // K0/2 (<= 32) cols: normalised input as packed bf16 (A of L0)
 
 enum {
-  B_FULL = 0,        // [NSTAGE] weight stage landed (tx)
-  B_EMPTY = 3,       // [NSTAGE] weight stage consumed (commit)
-  B_W2FULL = 6,
-  B_W2EMPTY = 7,
-  B_W0RES = 8,
-  B_ZREADY = 9,      // Z operand tile written (128 arrivals)
-  B_ACC0FULL = 10,   // [2] L0 chunk accumulated (commit)
-  B_H0FULL = 12,     // [2] H0 operand tile written (128 arrivals)
-  B_H0FREE = 14,     // [2] H0 operand tile consumed (commit)
-  B_ACC1FULL = 16,
-  B_ACC1FREE = 17,   // acc1 drained to registers (128 arrivals)
-  B_H1FULL = 18,     // [2]
-  B_H1FREE = 20,     // [2]
-  B_ACC2FULL = 22,
-  NUM_BARS = 23
+  B_FULL = 0,        // [NSTAGE] W1 stage landed (tx)
+  B_EMPTY = 4,       // [NSTAGE] W1 stage consumed (commit)
+  B_W2FULL = 8,
+  B_W2EMPTY = 9,
+  B_W0FULL = 10,     // [2] W0 group tile landed (tx)
+  B_W0EMPTY = 12,    // [2] W0 group tile consumed (commit)
+  B_ZREADY = 14,     // Z operand written (128 arrivals)
+  B_ACC0FULL = 15,   // L0 group accumulated (commit)
+  B_ACC0FREE = 16,   // acc0 loaded to registers (128 arrivals)
+  B_H0FULL = 17,     // [2] H0 operand written to TMEM (128 arrivals)
+  B_H0FREE = 19,     // [2] H0 operand consumed (commit)
+  B_ACC1FULL = 21,   // layer-1 pass accumulated (commit)
+  B_H1FULL = 22,     // [4] 64-column slice of acc1 converted in place (128 arrivals)
+  B_ACC2FULL = 26,
+  NUM_BARS = 27
 };
 
 struct PolicyLayer {
@@ -86,11 +95,11 @@ struct KParams {
   int NC, KC;
   int n_steps, n_slots, n_tiles;
   int resume;            // 1: state comes from row_state (B1 step / continued run)
-  // packed weights (per model: stages | W2 chunks | resident W0 tiles)
+  // packed weights (per model: W1 stages | W2 chunks | W0 group tiles)
   const uint8_t* wstream;
   unsigned long long model_stride;
-  uint32_t stage_bytes, w0tile_bytes, w2chunk_bytes, off_w2, off_w0res;
-  const float* bias;     // [K][2H + 32]: b0 | b1 | b2 (zero padded)
+  uint32_t stage_bytes, w0g_bytes, w2chunk_bytes, off_w2, off_w0g;   // w0g: [128 n][K0] tile
+  const float* bias;     // [K][2H + 32]: b0 (unused by the kernel) | b1 | b2 (zero padded)
   const float* norm;     // in_mean[SA] | in_std[SA] | diff_mean[S] | diff_std[S]
   const float* pol;      // policy blob (padded W, b per layer, then log_std[AMAX])
   int pol_floats, n_pol_layers, pol_out_tanh, pol_logstd_off;
@@ -114,13 +123,12 @@ struct KParams {
   int* row_ts;            // [n_tiles*128]
   int* row_nreset;        // [n_tiles*128]
   unsigned* tile_flag;    // [n_tiles]
-  unsigned long long* trace;   // optional event trace of one CTA (dev tool), or nullptr
+  unsigned long long* trace;   // optional event trace of one CTA (METRPO_TRACE builds), or nullptr
   int trace_cta, trace_t0, trace_t1;
   unsigned* dbg;          // [DBG_HEADER + grid*6*4] abort flag + wait records
   const int4* segs;       // [n_slots][MAX_SEG] = (tile, t0, t1, wait_flag); tile < 0 -> unused
   // smem carve-up (byte offsets from the 1024-aligned base)
-  uint32_t off_stage, off_sw0res, off_z, off_h0, off_h1, off_sw2, off_sbias, off_snorm, off_spol,
-      off_bars;
+  uint32_t off_stage, off_sw0g, off_scr, off_sw2, off_sbias, off_snorm, off_spol, off_bars;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -154,9 +162,8 @@ __device__ __forceinline__ void dbg_record(unsigned* dbg, uint32_t tag, uint32_t
   dbg[idx + 2] = why;    // 1 = timed out here, 2 = saw the abort flag here
   dbg[idx + 3] = threadIdx.x;
 }
-__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, unsigned* dbg, uint32_t tag,
-                                         uint32_t info) {
-  if (mbar_try_wait(bar, parity)) return true;
+__device__ __noinline__ bool wait_bar_slow(uint64_t* bar, uint32_t parity, unsigned* dbg, uint32_t tag,
+                                           uint32_t info) {
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -171,8 +178,13 @@ __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, unsigne
   }
   return true;
 }
-__device__ __forceinline__ bool wait_ge(const unsigned* ptr, unsigned target, unsigned* dbg, uint32_t tag,
-                                        uint32_t info) {
+__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, unsigned* dbg, uint32_t tag,
+                                         uint32_t info) {
+  if (mbar_try_wait(bar, parity)) return true;
+  return wait_bar_slow(bar, parity, dbg, tag, info);
+}
+__device__ __noinline__ bool wait_ge(const unsigned* ptr, unsigned target, unsigned* dbg, uint32_t tag,
+                                     uint32_t info) {
   if (ld_acquire_gpu(ptr) >= target) return true;
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
@@ -188,18 +200,24 @@ __device__ __forceinline__ bool wait_ge(const unsigned* ptr, unsigned target, un
   }
   return true;
 }
-#define WAITB(idx, par, info) \
-  do { if (!wait_bar(&bars[idx], (par), p.dbg, (idx), (info))) goto bail; } while (0)
+#define WAITB(idx, par) \
+  do { if (!wait_bar(&bars[idx], (par), p.dbg, (idx), (uint32_t)st_dbg)) goto bail; } while (0)
 
-// optional event trace (dev tool): role-private logs of (code << 40 | clock) for one CTA and a
-// window of steps; enabled by metrpo_rollout_set_trace.  role 0 producer, 1 MMA, 2 epilogue.
+// optional event trace (dev tool, -DMETRPO_TRACE): role-private logs of (code << 40 | clock) for
+// one CTA and a window of steps.  role 0 producer, 1 MMA, 2 epilogue.
 constexpr int TRACE_CAP = 4096;
+#ifdef METRPO_TRACE
 #define TRACE(role, code)                                                                    \
   do {                                                                                       \
     if (tr_on && tr_n < TRACE_CAP)                                                           \
       p.trace[(role) * TRACE_CAP + tr_n++] =                                                 \
           (static_cast<unsigned long long>(code) << 40) | (clock64() & 0xFFFFFFFFFFull);     \
   } while (0)
+#define TRACE_ON(cond) tr_on = p.trace && blockIdx.x == p.trace_cta && (cond)
+#else
+#define TRACE(role, code) do { } while (0)
+#define TRACE_ON(cond) do { } while (0)
+#endif
 
 // per-row analytic cost (reward = -cost); u is the clipped action.  envs/com_*_env.py
 __device__ __forceinline__ float env_cost(int env_id, int S, int A, const float (&xn)[SMAX],
@@ -246,42 +264,79 @@ __device__ __forceinline__ bool env_is_done(int env_id, int S, const float (&xn)
 }
 
 // one dense layer of the policy on CUDA cores: thread r owns column r of the [n][128] scratch
+// (thread-private, so layers may run in place).  Packed FFMA2 (two fp32 FMAs per instruction).
+template <int NP>
+__device__ __forceinline__ void dense_fma_row(float2 (&acc2)[NP / 2], float xi, const float4 (&w)[NP / 4]) {
+  const float2 x2 = make_float2(xi, xi);
+#pragma unroll
+  for (int j = 0; j < NP / 4; ++j) {
+    acc2[2 * j] = __ffma2_rn(x2, make_float2(w[j].x, w[j].y), acc2[2 * j]);
+    acc2[2 * j + 1] = __ffma2_rn(x2, make_float2(w[j].z, w[j].w), acc2[2 * j + 1]);
+  }
+}
+template <int NP>
+__device__ __forceinline__ void dense_load_row(const float* in_s, const float* W, int i, int r, float& xi,
+                                               float4 (&w)[NP / 4]) {
+  xi = in_s[i * TILE_M + r];
+  const float4* w4 = reinterpret_cast<const float4*>(W + i * NP);
+#pragma unroll
+  for (int j = 0; j < NP / 4; ++j) w[j] = w4[j];
+}
 template <int NP>
 __device__ __forceinline__ void dense_layer(const float* in_s, int nin, const float* W,
                                             const float* b, float (&acc)[NP], int r) {
+  float2 acc2[NP / 2];
 #pragma unroll
-  for (int j = 0; j < NP; ++j) acc[j] = b[j];
-  for (int i = 0; i < nin; ++i) {
-    const float xi = in_s[i * TILE_M + r];
-    const float4* w4 = reinterpret_cast<const float4*>(W + i * NP);
+  for (int j = 0; j < NP / 2; ++j) acc2[j] = make_float2(b[2 * j], b[2 * j + 1]);
+  float4 wa[NP / 4], wb[NP / 4];
+  float xa, xb;
+  dense_load_row<NP>(in_s, W, 0, r, xa, wa);
+  int i = 0;
+  for (; i + 2 < nin; i += 2) {          // weight rows i+1 / i+2 are in flight while row i / i+1 is used
+    dense_load_row<NP>(in_s, W, i + 1, r, xb, wb);
+    dense_fma_row<NP>(acc2, xa, wa);
+    dense_load_row<NP>(in_s, W, i + 2, r, xa, wa);
+    dense_fma_row<NP>(acc2, xb, wb);
+  }
+  if (i + 1 < nin) {
+    dense_load_row<NP>(in_s, W, i + 1, r, xb, wb);
+    dense_fma_row<NP>(acc2, xa, wa);
+    dense_fma_row<NP>(acc2, xb, wb);
+  } else {
+    dense_fma_row<NP>(acc2, xa, wa);
+  }
 #pragma unroll
-    for (int j = 0; j < NP / 4; ++j) {
-      float4 w = w4[j];
-      acc[4 * j + 0] = fmaf(xi, w.x, acc[4 * j + 0]);
-      acc[4 * j + 1] = fmaf(xi, w.y, acc[4 * j + 1]);
-      acc[4 * j + 2] = fmaf(xi, w.z, acc[4 * j + 2]);
-      acc[4 * j + 3] = fmaf(xi, w.w, acc[4 * j + 3]);
+  for (int j = 0; j < NP / 2; ++j) { acc[2 * j] = acc2[j].x; acc[2 * j + 1] = acc2[j].y; }
+}
+
+// (bias +) ReLU + bf16 pack of 64 accumulator columns -> 32 packed columns (A operand layout);
+// relu and the bf16x2 pack are one F2FP.RELU instruction per column pair
+template <bool kBias>
+__device__ __forceinline__ void relu_pack(const uint32_t (&v0)[32], const uint32_t (&v1)[32],
+                                          const float* bias, uint32_t (&pk)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {   // 8 columns per step
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = 8 * c + i;
+      a[i] = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]);
     }
+    if (kBias) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * c);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * c + 4);
+      a[0] += b0.x; a[1] += b0.y; a[2] += b0.z; a[3] += b0.w;
+      a[4] += b1.x; a[5] += b1.y; a[6] += b1.z; a[7] += b1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[4 * c + i] = relu_pack_bf16x2(a[2 * i], a[2 * i + 1]);
   }
 }
 
-// bias + ReLU + bf16 pack of 64 accumulator columns -> one SW128 row (8 x 16 B chunks)
-__device__ __forceinline__ void relu_pack_store(const uint32_t (&v0)[32], const uint32_t (&v1)[32],
-                                                const float* bias, uint8_t* tile, int row) {
-  const uint32_t rbase = (row >> 3) * 1024u + (row & 7u) * 128u;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint32_t pk[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int col = 8 * c + 2 * i;
-      float a0 = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]) + bias[col];
-      float a1 = __uint_as_float(col + 1 < 32 ? v0[col + 1] : v1[col + 1 - 32]) + bias[col + 1];
-      pk[i] = pack_bf16x2(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
-    }
-    *reinterpret_cast<uint4*>(tile + rbase + (((c ^ row) & 7) << 4)) =
-        make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  }
+// tanh(x) = 1 - 2/(exp(2x)+1) with ex2.approx / rcp.approx: abs error ~1e-7 (policy hidden layers)
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, e + 1.f);
 }
 
 // =============================================================================================
@@ -295,11 +350,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
   const int slot = blockIdx.x / p.K, k = blockIdx.x % p.K;
 
   uint8_t* sStage = smem + p.off_stage;
-  uint8_t* sW0res = smem + p.off_sw0res;
-  uint8_t* sZ = smem + p.off_z;
-  uint8_t* sH0 = smem + p.off_h0;
-  uint8_t* sH1 = smem + p.off_h1;
+  uint8_t* sW0g = smem + p.off_sw0g;     // 2-slot ring of W0 group tiles
   uint8_t* sW2 = smem + p.off_sw2;
+  float* sScr = reinterpret_cast<float*>(smem + p.off_scr);   // [max(S+A,32)][128] fp32 scratch
   float* sBias = reinterpret_cast<float*>(smem + p.off_sbias);
   float* sNorm = reinterpret_cast<float*>(smem + p.off_snorm);
   float* sPol = reinterpret_cast<float*>(smem + p.off_spol);
@@ -315,19 +368,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
 
   // ---- one-time setup ----
   int st_dbg = 0;   // progress counter reported by the wait diagnostics
+#ifdef METRPO_TRACE
   bool tr_on = false;
   int tr_n = 0;
+#endif
   if (tid == 0) {
     abort_smem = 0;
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
-    mbar_init(&bars[B_W2FULL], 1); mbar_init(&bars[B_W2EMPTY], 1); mbar_init(&bars[B_W0RES], 1);
+    mbar_init(&bars[B_W2FULL], 1); mbar_init(&bars[B_W2EMPTY], 1);
     mbar_init(&bars[B_ZREADY], EPI_THREADS);
+    mbar_init(&bars[B_ACC0FULL], 1); mbar_init(&bars[B_ACC0FREE], EPI_THREADS);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars[B_ACC0FULL + i], 1); mbar_init(&bars[B_H0FULL + i], EPI_THREADS);
-      mbar_init(&bars[B_H0FREE + i], 1); mbar_init(&bars[B_H1FULL + i], EPI_THREADS);
-      mbar_init(&bars[B_H1FREE + i], 1);
+      mbar_init(&bars[B_W0FULL + i], 1); mbar_init(&bars[B_W0EMPTY + i], 1);
+      mbar_init(&bars[B_H0FULL + i], EPI_THREADS); mbar_init(&bars[B_H0FREE + i], 1);
     }
-    mbar_init(&bars[B_ACC1FULL], 1); mbar_init(&bars[B_ACC1FREE], EPI_THREADS);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[B_H1FULL + i], EPI_THREADS);
+    mbar_init(&bars[B_ACC1FULL], 1);
     mbar_init(&bars[B_ACC2FULL], 1);
     fence_mbar_init();
   }
@@ -335,7 +391,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
   {  // constants -> smem (generic loads; read-only for the rest of the kernel)
     const float* gb = p.bias + static_cast<size_t>(k) * (2 * p.H + 32);
     for (int i = tid; i < 2 * p.H + 32; i += NUM_THREADS) sBias[i] = gb[i];
-    for (int i = tid; i < 2 * p.SA + 2 * p.S; i += NUM_THREADS) sNorm[i] = p.norm[i];
+    for (int i = tid; i < 2 * p.SA + 2 * p.S; i += NUM_THREADS) {
+      const float v = p.norm[i];
+      sNorm[i] = (i >= p.SA && i < 2 * p.SA) ? __frcp_rn(v) : v;   // in_std slot holds 1 / in_std
+    }
     for (int i = tid; i < p.pol_floats; i += NUM_THREADS) sPol[i] = p.pol[i];
   }
   tc_fence_before();
@@ -349,26 +408,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
       if (lane == 0) {
         const uint8_t* wm = p.wstream + static_cast<size_t>(k) * p.model_stride;
         const uint64_t pol = l2_policy_evict_last();
-        mbar_arrive_expect_tx(&bars[B_W0RES], 2 * p.w0tile_bytes);
-        bulk_g2s_hint(sW0res, wm + p.off_w0res, 2 * p.w0tile_bytes, &bars[B_W0RES], pol);
-        uint32_t gs = 0, w2n = 0;
+        uint32_t s = 0, sphase = 0, w2n = 0, wg = 0;
+        const int NG = p.KC / 2;                      // L0 groups (2 chunks) per pass
+        const uint32_t total_groups = static_cast<uint32_t>(total_steps) * (NCH / 2);
         const int w2_at = p.KC > 3 ? 3 : p.KC - 1;
+        // W0 group tiles are consumed in the cyclic order wg % NG over the whole kernel; they are
+        // loaded one group ahead of the W1 stages of the group that precedes them.
+#define LOAD_W0()                                                                             \
+  do {                                                                                        \
+    if (wg < total_groups) {                                                                  \
+      const uint32_t ws = wg & 1;                                                             \
+      WAITB(B_W0EMPTY + ws, ((wg >> 1) & 1) ^ 1);                                             \
+      mbar_arrive_expect_tx(&bars[B_W0FULL + ws], p.w0g_bytes);                               \
+      bulk_g2s_hint(sW0g + ws * p.w0g_bytes,                                                  \
+                    wm + p.off_w0g + static_cast<size_t>(wg % NG) * p.w0g_bytes, p.w0g_bytes, \
+                    &bars[B_W0FULL + ws], pol);                                               \
+      ++wg;                                                                                   \
+    }                                                                                         \
+  } while (0)
+        LOAD_W0();
         for (int st = 0; st < total_steps; ++st) {
+          TRACE_ON(st >= p.trace_t0 && st < p.trace_t1);
+          const uint8_t* src = wm;
           for (int nc = 0; nc < p.NC; ++nc) {
             for (int kc = 0; kc < p.KC; ++kc) {
               st_dbg = (st << 8) | (nc * p.KC + kc);
-              tr_on = p.trace && blockIdx.x == p.trace_cta && st >= p.trace_t0 && st < p.trace_t1;
-              const uint32_t s = gs % NSTAGE, n = gs / NSTAGE;
+              if ((kc & 1) == 0) LOAD_W0();
               TRACE(0, 0x100 | (nc * p.KC + kc));
-              WAITB(B_EMPTY + s, (n & 1) ^ 1, (uint32_t)st_dbg);
+              WAITB(B_EMPTY + s, sphase ^ 1);
               TRACE(0, 0x200 | (nc * p.KC + kc));
               mbar_arrive_expect_tx(&bars[B_FULL + s], p.stage_bytes);
-              bulk_g2s_hint(sStage + s * p.stage_bytes,
-                            wm + static_cast<size_t>(nc * p.KC + kc) * p.stage_bytes, p.stage_bytes,
-                            &bars[B_FULL + s], pol);
-              ++gs;
+              bulk_g2s_hint(sStage + s * p.stage_bytes, src, p.stage_bytes, &bars[B_FULL + s], pol);
+              src += p.stage_bytes;
+              if (++s == NSTAGE) { s = 0; sphase ^= 1; }
               if (kc == w2_at) {
-                WAITB(B_W2EMPTY, (w2n & 1) ^ 1, (uint32_t)st_dbg);
+                WAITB(B_W2EMPTY, (w2n & 1) ^ 1);
                 mbar_arrive_expect_tx(&bars[B_W2FULL], p.w2chunk_bytes);
                 bulk_g2s_hint(sW2, wm + p.off_w2 + static_cast<size_t>(nc) * p.w2chunk_bytes,
                               p.w2chunk_bytes, &bars[B_W2FULL], pol);
@@ -380,96 +454,187 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
       }
     } else if (warp == 1) {
       // =========================== MMA issuer ===========================
-      if (lane == 0) {
-        const uint32_t idesc0 = idesc_bf16_f32(128, 64);
+      // All 32 lanes run the (warp-uniform) loop so that descriptors live in uniform registers;
+      // lanes 0/1 poll the mbarriers, one elected lane issues tcgen05.mma / commit.  The tensor
+      // pipe accepts only a couple of queued MMAs before issue blocks, so every cycle this warp
+      // spends waiting is pipe idle time: the next chunk's barriers are probed while the current
+      // chunk's MMAs are still queued.
+      {
+        const uint32_t idesc0 = idesc_bf16_f32(128, 128);
         const uint32_t idesc1 = idesc_bf16_f32(128, 256);
         const uint32_t idesc2 = idesc_bf16_f32(128, p.S_pad);
         const int k0steps = p.K0 / 16;
-        const uint64_t zdesc = smem_desc_noswz(smem_u32(sZ), TILE_M * 16, 128);
-        const uint32_t z_kstep = (2 * TILE_M * 16) >> 4;     // descriptor-lo units per 16-k step
-        const uint32_t w0_kstep = (2 * 64 * 16) >> 4;
-        const uint64_t h0desc[2] = {smem_desc_sw128(smem_u32(sH0)),
-                                    smem_desc_sw128(smem_u32(sH0 + H_TILE_BYTES))};
-        const uint64_t h1desc[2] = {smem_desc_sw128(smem_u32(sH1)),
-                                    smem_desc_sw128(smem_u32(sH1 + H_TILE_BYTES))};
+        const uint32_t ztm = tmem + TM_Z;                    // A of L0: 8 TMEM columns per 16-k step
+        const uint32_t w0_kstep = (2 * 128 * 16) >> 4;       // W0 group tile: [128 n][K0] no-swizzle
+        const uint64_t w0desc0 = smem_desc_noswz(smem_u32(sW0g), 128 * 16, 128);
+        const uint32_t w0slot = p.w0g_bytes >> 4;
         const uint64_t w2desc = smem_desc_sw128(smem_u32(sW2));
         const uint32_t w2_sub = (p.S_pad * 128) >> 4;
-        uint64_t stdesc[NSTAGE], stw0desc[NSTAGE];
-        for (int s = 0; s < NSTAGE; ++s) {
-          stdesc[s] = smem_desc_sw128(smem_u32(sStage + s * p.stage_bytes));
-          stw0desc[s] = smem_desc_noswz(smem_u32(sStage + s * p.stage_bytes + W1_TILE_BYTES), 64 * 16, 128);
-        }
-        const uint64_t w0resdesc[2] = {
-            smem_desc_noswz(smem_u32(sW0res), 64 * 16, 128),
-            smem_desc_noswz(smem_u32(sW0res + p.w0tile_bytes), 64 * 16, 128)};
-        const uint32_t acc1 = tmem + TM_ACC1, acc2 = tmem + TM_ACC2;
+        const uint64_t stdesc0 = smem_desc_sw128(smem_u32(sStage));
+        const uint32_t ststride = p.stage_bytes >> 4;
+        const uint32_t acc0 = tmem + TM_ACC0, acc1 = tmem + TM_ACC1, acc2 = tmem + TM_ACC2;
 
-        uint32_t gs = 0, gc = 0, hs = 0, zn = 0, a1f = 0, w2n = 0;
-        WAITB(B_W0RES, 0, (uint32_t)st_dbg);
+#define WAITW1(idx, par)                                                                      \
+  do {                                                                                        \
+    bool ok_ = true;                                                                          \
+    if (lane == 0) ok_ = wait_bar(&bars[idx], (par), p.dbg, (idx), (uint32_t)st_dbg);         \
+    if (!__all_sync(0xffffffffu, ok_)) goto bail;                                             \
+  } while (0)
+#define WAITW2(idxa, para, idxb, parb)                                                        \
+  do {                                                                                        \
+    bool ok_ = true;                                                                          \
+    const int wi_ = lane == 0 ? (idxa) : (idxb);                                              \
+    const uint32_t wp_ = lane == 0 ? (para) : (parb);                                         \
+    if (lane < 2) ok_ = wait_bar(&bars[wi_], wp_, p.dbg, (uint32_t)wi_, (uint32_t)st_dbg);    \
+    if (!__all_sync(0xffffffffu, ok_)) goto bail;                                             \
+  } while (0)
+// single non-blocking probe of up to four barriers: lanes 0..3 each test their own barrier with ONE
+// (data-divergent, not control-divergent) try_wait; idx < 0 -> lane idle.  Result consumed later.
+#define PROBE4(var, i0, p0, i1, p1, i2, p2, i3, p3)                                           \
+  bool var = true;                                                                            \
+  {                                                                                           \
+    const int wi_ = lane == 0 ? (i0) : lane == 1 ? (i1) : lane == 2 ? (i2) : lane == 3 ? (i3) : -1; \
+    const uint32_t wp_ = lane == 0 ? (p0) : lane == 1 ? (p1) : lane == 2 ? (p2) : (p3);       \
+    if (wi_ >= 0) var = mbar_try_wait(&bars[wi_], wp_);                                       \
+  }
+// blocking wait on up to four barriers in parallel (lanes 0..3); idx < 0 -> lane idle
+#define WAITW4(i0, p0, i1, p1, i2, p2, i3, p3)                                                \
+  do {                                                                                        \
+    bool ok_ = true;                                                                          \
+    const int wi_ = lane == 0 ? (i0) : lane == 1 ? (i1) : lane == 2 ? (i2) : lane == 3 ? (i3) : -1; \
+    const uint32_t wp_ = lane == 0 ? (p0) : lane == 1 ? (p1) : lane == 2 ? (p2) : (p3);       \
+    if (wi_ >= 0) ok_ = wait_bar(&bars[wi_], wp_, p.dbg, (uint32_t)wi_, (uint32_t)st_dbg);    \
+    if (!__all_sync(0xffffffffu, ok_)) goto bail;                                             \
+  } while (0)
+
+        uint32_t s = 0, sphase = 0;   // W1 stage ring position / phase
+        uint32_t gg = 0;              // L0 groups issued so far (acc0 / W0 ring use count)
+        uint32_t hg = 0;              // groups consumed by L1 so far (H0 buffer use count)
+        uint32_t zn = 0, npass = 0, w2n = 0;
+        const int NG = p.KC / 2;      // groups per pass
+        const int NGS = NCH / 2;      // groups per step
         for (int st = 0; st < total_steps; ++st) {
-          tr_on = p.trace && blockIdx.x == p.trace_cta && st >= p.trace_t0 && st < p.trace_t1;
+          TRACE_ON(lane == 0 && st >= p.trace_t0 && st < p.trace_t1);
           TRACE(1, 0x1000);
-          WAITB(B_ZREADY, zn & 1, (uint32_t)st_dbg); ++zn;
+          // step prologue: Z ready, W0 tile of the step's first group, acc0 drained
+          WAITW4(B_ZREADY, zn & 1, B_W0FULL + (int)(gg & 1), (gg >> 1) & 1,
+                 gg > 0 ? B_ACC0FREE : -1, (gg - 1) & 1, -1, 0);
+          ++zn;
           TRACE(1, 0x1001);
           tc_fence_after();
-          // prologue: L0 of chunks 0 and 1 from the resident W0 tiles
-          for (int c = 0; c < 2 && c < NCH; ++c) {
-            const uint32_t b = (gc + c) & 1;
+          if (elect_one()) {
             for (int j = 0; j < k0steps; ++j)
-              umma_ss(tmem + TM_ACC0 + b * 64, zdesc + j * z_kstep, w0resdesc[c] + j * w0_kstep,
-                      idesc0, j > 0);
-            umma_commit(&bars[B_ACC0FULL + b]);
+              umma_ts(acc0, ztm + j * 8, w0desc0 + (gg & 1) * w0slot + j * w0_kstep, idesc0, j > 0);
+            umma_commit(&bars[B_ACC0FULL]);
+            umma_commit(&bars[B_W0EMPTY + (gg & 1)]);
           }
-          for (int nc = 0; nc < p.NC; ++nc) {
-            for (int kc = 0; kc < p.KC; ++kc) {
-              const int g = nc * p.KC + kc;
-              st_dbg = (st << 8) | g;
-              const uint32_t b = gc & 1, s = gs % NSTAGE;
-              TRACE(1, 0x100 | g);
-              WAITB(B_FULL + s, (gs / NSTAGE) & 1, (uint32_t)st_dbg);
-              TRACE(1, 0x200 | g);
-              WAITB(B_H0FULL + b, (gc >> 1) & 1, (uint32_t)st_dbg);
-              TRACE(1, 0x300 | g);
-              tc_fence_after();
-              if (g + 2 < NCH) {   // L0 of chunk g+2 (its W0 tile rides in this stage)
+          __syncwarp();
+          ++gg;
+          // operands of group 0 (chunk a) + what the L0 of group 1 needs
+          WAITW4(B_FULL + (int)s, sphase, B_H0FULL + 0, hg & 1,
+                 NGS > 1 ? B_ACC0FREE : -1, (gg - 1) & 1, NGS > 1 ? B_W0FULL + (int)(gg & 1) : -1, (gg >> 1) & 1);
+          int gp = 0, nc = 0;   // group position inside the pass / pass index
+          for (int G = 0; G < NGS; ++G) {
+            st_dbg = (st << 8) | (2 * G);
+            const bool next_l0 = (G + 1 < NGS);
+            const bool first_of_pass = (gp == 0), last_of_pass = (gp == NG - 1);
+            uint32_t s1 = s + 1, sphase1 = sphase;
+            if (s1 == NSTAGE) { s1 = 0; sphase1 ^= 1; }
+            uint32_t s2 = s1 + 1, sphase2 = sphase1;
+            if (s2 == NSTAGE) { s2 = 0; sphase2 ^= 1; }
+            TRACE(1, 0x100 | (2 * G));
+            // ---- batch 1: L0 of the next group (its epilogue needs a full group of lead time),
+            //      then L1 of chunk a
+            tc_fence_after();
+            if (elect_one()) {
+              if (next_l0) {
                 for (int j = 0; j < k0steps; ++j)
-                  umma_ss(tmem + TM_ACC0 + b * 64, zdesc + j * z_kstep, stw0desc[s] + j * w0_kstep,
-                          idesc0, j > 0);
-                umma_commit(&bars[B_ACC0FULL + b]);
+                  umma_ts(acc0, ztm + j * 8, w0desc0 + (gg & 1) * w0slot + j * w0_kstep, idesc0, j > 0);
+                umma_commit(&bars[B_ACC0FULL]);
+                umma_commit(&bars[B_W0EMPTY + (gg & 1)]);
               }
-              if (kc == 0) {
-                // acc1 is drained once per pass: pass n (global count) waits for drain n-1
-                if (a1f > 0) {
-                  WAITB(B_ACC1FREE, (a1f - 1) & 1, (uint32_t)st_dbg);
-                  tc_fence_after();
-                }
-                ++a1f;
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma_ss(acc1, h0desc[b] + 2 * j, stdesc[s] + 2 * j, idesc1, (kc | j) != 0);
+              const uint32_t at = tmem + TM_H0;
+              const uint64_t bd = stdesc0 + s * ststride;
+              umma_ts(acc1, at, bd, idesc1, first_of_pass ? 0u : 1u);
+              umma_ts(acc1, at + 8, bd + 2, idesc1, 1);
+              umma_ts(acc1, at + 16, bd + 4, idesc1, 1);
+              umma_ts(acc1, at + 24, bd + 6, idesc1, 1);
               umma_commit(&bars[B_EMPTY + s]);
-              umma_commit(&bars[B_H0FREE + b]);
-              if (kc == p.KC - 1) umma_commit(&bars[B_ACC1FULL]);
-              TRACE(1, 0x400 | g);
-              ++gs; ++gc;
+              umma_commit(&bars[B_H0FREE + 0]);
             }
-            // L2 of pass nc: acc2 += relu(h1 chunk) * W2 chunk
-            WAITB(B_W2FULL, w2n & 1, (uint32_t)st_dbg); ++w2n;
-            for (int sub = 0; sub < 4; ++sub) {
-              const uint32_t bb = hs & 1;
-              WAITB(B_H1FULL + bb, (hs >> 1) & 1, (uint32_t)st_dbg);
+            __syncwarp();
+            if (next_l0) ++gg;
+            // ---- chunk b operands (probe; the MMAs above are still executing)
+            {
+              PROBE4(rb, B_FULL + (int)s1, sphase1, B_H0FULL + 1, hg & 1, -1, 0, -1, 0);
+              if (!__all_sync(0xffffffffu, rb)) WAITW4(B_FULL + (int)s1, sphase1, B_H0FULL + 1, hg & 1, -1, 0, -1, 0);
+            }
+            TRACE(1, 0x300 | (2 * G));
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t at = tmem + TM_H0 + 32;
+              const uint64_t bd = stdesc0 + s1 * ststride;
+              umma_ts(acc1, at, bd, idesc1, 1);
+              umma_ts(acc1, at + 8, bd + 2, idesc1, 1);
+            }
+            __syncwarp();
+            // ---- probe everything the next group needs while the MMAs above are queued
+            const bool need_l0_2 = (G + 2 < NGS);
+            const bool has_next = (G + 1 < NGS);
+            PROBE4(rn, has_next ? B_FULL + (int)s2 : -1, sphase2, has_next ? B_H0FULL + 0 : -1, (hg + 1) & 1,
+                   need_l0_2 ? B_ACC0FREE : -1, (gg - 1) & 1,
+                   need_l0_2 ? B_W0FULL + (int)(gg & 1) : -1, (gg >> 1) & 1);
+            if (elect_one()) {
+              const uint32_t at = tmem + TM_H0 + 32;
+              const uint64_t bd = stdesc0 + s1 * ststride;
+              umma_ts(acc1, at + 16, bd + 4, idesc1, 1);
+              umma_ts(acc1, at + 24, bd + 6, idesc1, 1);
+              umma_commit(&bars[B_EMPTY + s1]);
+              umma_commit(&bars[B_H0FREE + 1]);
+              if (last_of_pass) umma_commit(&bars[B_ACC1FULL]);
+            }
+            __syncwarp();
+            TRACE(1, 0x400 | (2 * G));
+            if (last_of_pass) {
+              // L2 of pass nc: acc2 += H1 (converted in place in acc1's columns) * W2 chunk.
+              // The next pass's L1 overwrites acc1 only after these MMAs (same issuing thread,
+              // in-order pipe), so no "acc1 free" barrier is needed.
+              TRACE(1, 0x2000 | nc);
+              // all four 64-column slices must be converted; one wait round, one MMA batch
+              WAITW4(B_H1FULL + 0, npass & 1, B_H1FULL + 1, npass & 1, B_H1FULL + 2, npass & 1,
+                     B_H1FULL + 3, npass & 1);
+              WAITW1(B_W2FULL, w2n & 1); ++w2n;
+              TRACE(1, 0x2200 | (nc << 4));
               tc_fence_after();
+              if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma_ss(acc2, h1desc[bb] + 2 * j, w2desc + sub * w2_sub + 2 * j, idesc2,
-                        (nc | sub | j) != 0);
-              umma_commit(&bars[B_H1FREE + bb]);
-              ++hs;
+                for (int sub = 0; sub < 4; ++sub) {
+                  const uint32_t at = acc1 + sub * 64;
+                  const uint64_t bd = w2desc + sub * w2_sub;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) umma_ts(acc2, at + 8 * j, bd + 2 * j, idesc2, (nc | sub | j) != 0);
+                }
+              }
+              __syncwarp();
+              TRACE(1, 0x2400 | (nc << 4));
+              if (elect_one()) umma_commit(&bars[B_W2EMPTY]);
+              __syncwarp();
+              TRACE(1, 0x2300 | nc);
+              ++npass; ++nc; gp = 0;
+            } else {
+              ++gp;
             }
-            umma_commit(&bars[B_W2EMPTY]);
+            if (G + 1 < NGS && !__all_sync(0xffffffffu, rn)) {
+              WAITW4(B_FULL + (int)s2, sphase2, B_H0FULL + 0, (hg + 1) & 1,
+                     need_l0_2 ? B_ACC0FREE : -1, (gg - 1) & 1,
+                     need_l0_2 ? B_W0FULL + (int)(gg & 1) : -1, (gg >> 1) & 1);
+            }
+            TRACE(1, 0x500 | (2 * G));
+            ++hg;
+            s = s2; sphase = sphase2;
           }
-          umma_commit(&bars[B_ACC2FULL]);
+          if (elect_one()) umma_commit(&bars[B_ACC2FULL]);
+          __syncwarp();
           TRACE(1, 0x1002);
         }
       }
@@ -479,22 +644,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
       const int r = (warp & 3) * 32 + lane;                // TMEM lane == row inside the tile
       const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
       const int S = p.S, A = p.A, K = p.K;
-      const float* sB0 = sBias;
       const float* sB1 = sBias + p.H;
       const float* sB2 = sBias + 2 * p.H;
       const float* inMean = sNorm;
-      const float* inStd = sNorm + p.SA;
+      const float* inRstd = sNorm + p.SA;   // 1 / in_std
       const float* dMean = sNorm + 2 * p.SA;
       const float* dStd = sNorm + 2 * p.SA + S;
-      float* scrA = reinterpret_cast<float*>(sH0);         // [<=64][128] fp32 scratch (32 KB)
-      float* scrB = reinterpret_cast<float*>(sH1);         // 2 x [32][128] fp32 scratch
-      float* scrC = scrB + 32 * TILE_M;
+      float* scrA = sScr;
 
-      uint32_t gc = 0, hs = 0, a1n = 0, a2n = 0, xn_cnt = 0;
+      uint32_t gg = 0, a1n = 0, a2n = 0, xn_cnt = 0;   // gg: L0 groups consumed so far
       float x[SMAX], a_raw[AMAX], a_mean[AMAX];
 #pragma unroll
       for (int s = 0; s < SMAX; ++s) x[s] = 0.f;
       int ts = 0, nreset = 0;
+      int est = 0;   // steps done by this CTA (trace window index, same as the MMA warp's st)
 
       for (int si = 0; si < MAX_SEG; ++si) {
         const int4 sg = segs[si];
@@ -522,7 +685,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
         }
 
         for (int t = t0; t < t1; ++t) {
-          tr_on = p.trace && blockIdx.x == p.trace_cta && e == 0 && (t - t0) >= p.trace_t0 && (t - t0) < p.trace_t1;
+          TRACE_ON(e == 0 && est >= p.trace_t0 && est < p.trace_t1);
+          ++est;
           TRACE(2, 0x1000);
           // ================= begin step: action + Z operand =================
           if (p.ext_actions != nullptr) {
@@ -532,29 +696,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               a_mean[i] = a_raw[i];
             }
           } else {
-            // policy mean network (training.py:99-103), fp32 on CUDA cores
+            // policy mean network (training.py:99-103), fp32 on CUDA cores, in place in scrA
 #pragma unroll
             for (int s = 0; s < SMAX; ++s)
               if (s < S) scrA[s * TILE_M + r] = x[s];
-            const float* in_s = scrA;
-            float* out_s = scrB;
             for (int l = 0; l < p.n_pol_layers; ++l) {
               const PolicyLayer L = p.pl[l];
               const bool last = (l == p.n_pol_layers - 1);
               if (!last) {
                 float acc[HPMAX];
-                dense_layer<HPMAX>(in_s, L.nin, sPol + L.w_off, sPol + L.b_off, acc, r);
+                dense_layer<HPMAX>(scrA, L.nin, sPol + L.w_off, sPol + L.b_off, acc, r);
 #pragma unroll
-                for (int j = 0; j < HPMAX; ++j) out_s[j * TILE_M + r] = tanhf(acc[j]);
-                in_s = out_s;
-                out_s = (out_s == scrB) ? scrC : scrB;
+                for (int j = 0; j < HPMAX; ++j) scrA[j * TILE_M + r] = fast_tanh(acc[j]);
               } else {
                 float acc[AMAX];
-                dense_layer<AMAX>(in_s, L.nin, sPol + L.w_off, sPol + L.b_off, acc, r);
+                dense_layer<AMAX>(scrA, L.nin, sPol + L.w_off, sPol + L.b_off, acc, r);
 #pragma unroll
                 for (int i = 0; i < AMAX; ++i) a_mean[i] = p.pol_out_tanh ? tanhf(acc[i]) : acc[i];
               }
             }
+            TRACE(2, 0x1010);
             // a = eps * exp(log_std) + mean   (rllab get_actions)
             if (p.determ) {
 #pragma unroll
@@ -585,82 +746,99 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               }
             }
           }
-          // z = (concat(x, clip(a)) - in_mean) / in_std, drop leading cols  (training.py:228,146-154)
+          TRACE(2, 0x1011);
+          // z = (concat(x, clip(a)) - in_mean) * (1 / in_std), drop leading cols  (training.py:228,146-154)
 #pragma unroll
           for (int s = 0; s < SMAX; ++s)
-            if (s < S) scrA[s * TILE_M + r] = __fdiv_rn(__fsub_rn(x[s], inMean[s]), inStd[s]);
+            if (s < S) scrA[s * TILE_M + r] = __fmul_rn(__fsub_rn(x[s], inMean[s]), inRstd[s]);
 #pragma unroll
           for (int i = 0; i < AMAX; ++i)
             if (i < A) {
               const float u = fminf(fmaxf(a_raw[i], -1.f), 1.f);   // env_helpers.py:599
-              scrA[(S + i) * TILE_M + r] = __fdiv_rn(__fsub_rn(u, inMean[S + i]), inStd[S + i]);
+              scrA[(S + i) * TILE_M + r] = __fmul_rn(__fsub_rn(u, inMean[S + i]), inRstd[S + i]);
             }
-          for (int c = 0; c < p.K0 / 8; ++c) {
-            uint32_t pk[4];
+          TRACE(2, 0x1012);
+          for (int c = 0; c < p.K0 / 16; ++c) {   // 16 k per tcgen05.st: 8 columns of bf16 pairs
+            uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int f0 = 8 * c + 2 * i, f1 = f0 + 1;
-              const float z0 = f0 < p.Din ? scrA[(f0 + p.drop) * TILE_M + r] : 0.f;
-              const float z1 = f1 < p.Din ? scrA[(f1 + p.drop) * TILE_M + r] : 0.f;
+            for (int i = 0; i < 8; ++i) {
+              const int f0 = 16 * c + 2 * i, f1 = f0 + 1;
+              // columns Din, Din+1 are 1.0: they multiply the bf16 hi / lo parts of b0 in W0
+              const float z0 = f0 < p.Din ? scrA[(f0 + p.drop) * TILE_M + r] : (f0 < p.Din + 2 ? 1.f : 0.f);
+              const float z1 = f1 < p.Din ? scrA[(f1 + p.drop) * TILE_M + r] : (f1 < p.Din + 2 ? 1.f : 0.f);
               pk[i] = pack_bf16x2(z0, z1);
             }
-            *reinterpret_cast<uint4*>(sZ + c * (TILE_M * 16) + r * 16) =
-                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            tmem_st8(tmem + lane_base + TM_Z + c * 8, pk);
           }
-          fence_proxy_async_smem();
+          tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&bars[B_ZREADY]);
           TRACE(2, 0x1001);
 
-          // ================= per-chunk epilogues =================
-          for (int g = 0; g < NCH; ++g) {
-            st_dbg = (t << 8) | g;
-            {
-              const uint32_t b = gc & 1;
-              uint32_t v0[32], v1[32];
-              TRACE(2, 0x100 | g);
-              WAITB(B_ACC0FULL + b, (gc >> 1) & 1, (uint32_t)st_dbg);
-              TRACE(2, 0x200 | g);
-              tc_fence_after();
-              tmem_ld32(tmem + lane_base + TM_ACC0 + b * 64, v0);
-              tmem_ld32(tmem + lane_base + TM_ACC0 + b * 64 + 32, v1);
-              tmem_ld_wait();
-              TRACE(2, 0x300 | g);
-              WAITB(B_H0FREE + b, ((gc >> 1) & 1) ^ 1, (uint32_t)st_dbg);
-              TRACE(2, 0x400 | g);
-              relu_pack_store(v0, v1, sB0 + (g % p.KC) * 64, sH0 + b * H_TILE_BYTES, r);
-              TRACE(2, 0x500 | g);
-              fence_proxy_async_smem();
-              tc_fence_before();
-              mbar_arrive(&bars[B_H0FULL + b]);
-              TRACE(2, 0x600 | g);
-              ++gc;
-            }
-            // layer-1 pass epilogue.  Pass nc is drained after the first two chunks of pass nc+1
-            // have been staged (keeps the MMA warp fed across the pass boundary); the last pass
-            // right after its last chunk.  KC >= 4, so the two triggers never coincide.
-            int drain_nc = -1;
-            if (g == NCH - 1) drain_nc = p.NC - 1;
-            else if (g >= p.KC && (g % p.KC) == 1) drain_nc = g / p.KC - 1;
-            if (drain_nc >= 0) {
-              TRACE(2, 0x700 | g);
-              WAITB(B_ACC1FULL, a1n & 1, (uint32_t)st_dbg); ++a1n;
-              TRACE(2, 0x800 | g);
-              tc_fence_after();
-              for (int sub = 0; sub < 4; ++sub) {
-                uint32_t v0[32], v1[32];
-                tmem_ld32(tmem + lane_base + TM_ACC1 + sub * 64, v0);
-                tmem_ld32(tmem + lane_base + TM_ACC1 + sub * 64 + 32, v1);
+          // ================= per-group epilogues (2 chunks of 64 hidden columns) =================
+          {
+            const int NG = p.KC / 2, NGS = NCH / 2;
+            int egp = 0, enc = 0;   // group position inside the pass / pass index
+            for (int G = 0; G < NGS; ++G) {
+              st_dbg = (t << 8) | (2 * G);
+              {
+                uint32_t v0[32], v1[32], v2[32], v3[32], pk[32], pk2[32];
+                TRACE(2, 0x100 | (2 * G));
+                WAITB(B_ACC0FULL, gg & 1);
+                TRACE(2, 0x200 | (2 * G));
+                tc_fence_after();
+                tmem_ld32(tmem + lane_base + TM_ACC0, v0);
+                tmem_ld32(tmem + lane_base + TM_ACC0 + 32, v1);
+                tmem_ld32(tmem + lane_base + TM_ACC0 + 64, v2);
+                tmem_ld32(tmem + lane_base + TM_ACC0 + 96, v3);
                 tmem_ld_wait();
-                if (sub == 3) { tc_fence_before(); mbar_arrive(&bars[B_ACC1FREE]); }
-                const uint32_t bb = hs & 1;
-                WAITB(B_H1FREE + bb, ((hs >> 1) & 1) ^ 1, (uint32_t)st_dbg);
-                relu_pack_store(v0, v1, sB1 + drain_nc * 256 + sub * 64, sH1 + bb * H_TILE_BYTES, r);
-                fence_proxy_async_smem();
-                mbar_arrive(&bars[B_H1FULL + bb]);
-                ++hs;
+                tc_fence_before();
+                mbar_arrive(&bars[B_ACC0FREE]);        // next group's L0 may overwrite acc0
+                TRACE(2, 0x300 | (2 * G));
+                relu_pack<false>(v0, v1, nullptr, pk);
+                relu_pack<false>(v2, v3, nullptr, pk2);
+                WAITB(B_H0FREE + 0, (gg & 1) ^ 1);
+                tmem_st32(tmem + lane_base + TM_H0, pk);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[B_H0FULL + 0]);
+                TRACE(2, 0x400 | (2 * G));
+                WAITB(B_H0FREE + 1, (gg & 1) ^ 1);
+                tmem_st32(tmem + lane_base + TM_H0 + 32, pk2);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[B_H0FULL + 1]);
+                TRACE(2, 0x600 | (2 * G));
+                ++gg;
               }
-              TRACE(2, 0x900 | g);
+              // layer-1 pass epilogue.  Pass nc is drained after the first group of pass nc+1 has
+              // been staged (keeps the MMA warp fed across the pass boundary); the last pass right
+              // after its last group.
+              int drain_nc = -1;
+              if (G == NGS - 1) drain_nc = p.NC - 1;
+              else if (egp == 0 && enc > 0) drain_nc = enc - 1;
+              if (++egp == NG) { egp = 0; ++enc; }
+              if (drain_nc >= 0) {
+                TRACE(2, 0x700 | (2 * G));
+                WAITB(B_ACC1FULL, a1n & 1);
+                TRACE(2, 0x800 | (2 * G));
+                tc_fence_after();
+#pragma unroll 1
+                for (int sub = 0; sub < 4; ++sub) {
+                  uint32_t v0[32], v1[32], pk[32];
+                  tmem_ld32(tmem + lane_base + TM_ACC1 + sub * 64, v0);
+                  tmem_ld32(tmem + lane_base + TM_ACC1 + sub * 64 + 32, v1);
+                  tmem_ld_wait();
+                  relu_pack<true>(v0, v1, sB1 + drain_nc * 256 + sub * 64, pk);
+                  // in place: the 64 fp32 columns just read become 32 columns of bf16 pairs
+                  tmem_st32(tmem + lane_base + TM_ACC1 + sub * 64, pk);
+                  tmem_st_wait();
+                  tc_fence_before();
+                  mbar_arrive(&bars[B_H1FULL + sub]);
+                }
+                ++a1n;
+                TRACE(2, 0x900 | (2 * G));
+              }
             }
           }
 
@@ -669,7 +847,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           {
             uint32_t v[32];
             TRACE(2, 0x1002);
-            WAITB(B_ACC2FULL, a2n & 1, (uint32_t)st_dbg); ++a2n;
+            WAITB(B_ACC2FULL, a2n & 1); ++a2n;
             TRACE(2, 0x1003);
             tc_fence_after();
             tmem_ld32(tmem + lane_base + TM_ACC2, v);
@@ -691,13 +869,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
 #pragma unroll
             for (int s = 0; s < SMAX; ++s)
               if (s < S) xb[(k * S + s) * TILE_M + r] = cand[s];
-            __threadfence();
+            TRACE(2, 0x1020);
+            // CTA barrier orders the 128 threads' stores before thread 0's gpu-scope release
             named_bar_sync(1, EPI_THREADS);
+            TRACE(2, 0x1021);
             if (e == 0) {
               red_release_gpu_add(&p.xctr[slot], 1u);
+              TRACE(2, 0x1022);
               if (!wait_ge(&p.xctr[slot], static_cast<unsigned>(K) * (xn_cnt + 1), p.dbg, 101u,
                            (uint32_t)st_dbg))
                 abort_smem = 1;
+              TRACE(2, 0x1023);
             }
             named_bar_sync(1, EPI_THREADS);
             if (*reinterpret_cast<volatile int*>(&abort_smem)) goto bail;
@@ -767,6 +949,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               for (int s = 0; s < SMAX; ++s) xnext[s] = (s < S) ? scrA[s * TILE_M + r] : 0.f;
             }
           }
+          TRACE(2, 0x1024);
           // reward = -cost_np_vec(s, clip(a), s')   (env_helpers.py:601)
           float u[AMAX];
 #pragma unroll
@@ -820,7 +1003,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           }
           p.row_ts[tile * TILE_M + r] = ts;
           p.row_nreset[tile * TILE_M + r] = nreset;
-          __threadfence();
           named_bar_sync(1, EPI_THREADS);
           if (e == 0) red_release_gpu_add(&p.tile_flag[tile], 1u);
         }

@@ -8,7 +8,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmetrpo.so")
+LIB_PATH = os.environ.get("METRPO_LIB", os.path.join(_HERE, "libmetrpo.so"))   # METRPO_LIB: dev override (trace build)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "metrpo.h")
 
 MAX_POLICY_LAYERS = 4
@@ -53,6 +53,7 @@ _PROTOS = {
     "metrpo_rollout_status": (_i, [_vp, _vp]),
     "metrpo_rollout_set_trace": (_i, [_vp, _i, _i, _i]),
     "metrpo_rollout_get_trace": (_i, [_vp, _vp]),
+    "metrpo_bench_mma": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "metrpo_selftest_umma": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -80,9 +80,17 @@ def _matmul(h, W, dtype, mma):
 def dynamics_forward(m, norm, xu, S, drop, dtype=np.float32, mma="fp32"):
     """next_state[B,S] of one model for xu = concat([state, action], 1)  (training.py:218-269)."""
     xu = xu.astype(dtype)
-    z = (xu - norm["in_mean"].astype(dtype)) / norm["in_std"].astype(dtype)   # :228
+    if mma == "bf16":   # the kernel multiplies by the fp32 reciprocal of in_std (1 ulp from the quotient)
+        z = (xu - norm["in_mean"].astype(dtype)) * (np.float32(1.0) / norm["in_std"].astype(np.float32))
+    else:
+        z = (xu - norm["in_mean"].astype(dtype)) / norm["in_std"].astype(dtype)   # :228
     z = z[:, drop:]                                                           # :146-154
-    h = np.maximum(_matmul(z, m["W0"], dtype, mma) + m["b0"].astype(dtype), 0)  # :207-208 relu
+    b0 = m["b0"].astype(dtype)
+    if mma == "bf16":
+        # the kernel folds b0 into the layer-0 MMA as bf16 hi + lo parts (two constant-1 columns)
+        hi = bf16_round(m["b0"])
+        b0 = hi + bf16_round(m["b0"] - hi)
+    h = np.maximum(_matmul(z, m["W0"], dtype, mma) + b0, 0)                     # :207-208 relu
     h = np.maximum(_matmul(h, m["W1"], dtype, mma) + m["b1"].astype(dtype), 0)
     o = _matmul(h, m["W2"], dtype, mma) + m["b2"].astype(dtype)               # identity (:166)
     # tf.add(diff_rms.mean + diff_rms.std * nn_output, x)   (:257)
