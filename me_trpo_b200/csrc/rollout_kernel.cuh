@@ -50,7 +50,7 @@
 namespace metrpo {
 
 constexpr int TILE_M = 128;
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 4;     // must stay 4: the EMPTY barriers double as H0-buffer-free signals (stage & 1 == chunk & 1)
 constexpr int SMAX = 32;      // max state dim held in registers
 constexpr int AMAX = 8;       // max action dim
 constexpr int HPMAX = 32;     // max policy hidden width
@@ -68,21 +68,22 @@ constexpr uint32_t TM_Z = 480;       // K0/2 (<= 32) cols: normalised input as p
 
 enum {
   B_FULL = 0,        // [NSTAGE] W1 stage landed (tx)
-  B_EMPTY = 4,       // [NSTAGE] W1 stage consumed (commit)
+  B_EMPTY = 4,       // [NSTAGE] L1 of the chunk in this stage completed (commit): frees the W1 stage
+                     //          for the producer AND the H0 buffer (stage & 1) for the epilogue
   B_W2FULL = 8,
   B_W2EMPTY = 9,
   B_W0FULL = 10,     // [2] W0 group tile landed (tx)
-  B_W0EMPTY = 12,    // [2] W0 group tile consumed (commit)
+  B_ACC0FULL = 12,   // [2] L0 group accumulated (commit); also frees W0 ring slot (group & 1)
   B_ZREADY = 14,     // Z operand written (128 arrivals)
-  B_ACC0FULL = 15,   // L0 group accumulated (commit)
-  B_ACC0FREE = 16,   // acc0 loaded to registers (128 arrivals)
-  B_H0FULL = 17,     // [2] H0 operand written to TMEM (128 arrivals)
-  B_H0FREE = 19,     // [2] H0 operand consumed (commit)
-  B_ACC1FULL = 21,   // layer-1 pass accumulated (commit)
-  B_H1FULL = 22,     // [4] 64-column slice of acc1 converted in place (128 arrivals)
-  B_ACC2FULL = 26,
-  NUM_BARS = 27
+  B_ACC0FREE = 15,   // acc0 loaded to registers (128 arrivals)
+  B_H0FULL = 16,     // [2] H0 operand written to TMEM (128 arrivals)
+  B_ACC1FULL = 18,   // layer-1 pass accumulated (commit)
+  B_H1FULL = 19,     // [4] 64-column slice of acc1 converted in place (128 arrivals)
+  B_ACC2FULL = 23,
+  NUM_BARS = 24
 };
+// tcgen05.commit costs ~65 cycles in the (blocking) MMA issue stream, hence one barrier per event
+// with several waiters rather than one barrier per waiter.
 
 struct PolicyLayer {
   int nin, nout, npad;   // npad = 32 for hidden layers, 8 for the output layer
@@ -377,10 +378,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
     mbar_init(&bars[B_W2FULL], 1); mbar_init(&bars[B_W2EMPTY], 1);
     mbar_init(&bars[B_ZREADY], EPI_THREADS);
-    mbar_init(&bars[B_ACC0FULL], 1); mbar_init(&bars[B_ACC0FREE], EPI_THREADS);
+    mbar_init(&bars[B_ACC0FREE], EPI_THREADS);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars[B_W0FULL + i], 1); mbar_init(&bars[B_W0EMPTY + i], 1);
-      mbar_init(&bars[B_H0FULL + i], EPI_THREADS); mbar_init(&bars[B_H0FREE + i], 1);
+      mbar_init(&bars[B_W0FULL + i], 1); mbar_init(&bars[B_ACC0FULL + i], 1);
+      mbar_init(&bars[B_H0FULL + i], EPI_THREADS);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&bars[B_H1FULL + i], EPI_THREADS);
     mbar_init(&bars[B_ACC1FULL], 1);
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
   do {                                                                                        \
     if (wg < total_groups) {                                                                  \
       const uint32_t ws = wg & 1;                                                             \
-      WAITB(B_W0EMPTY + ws, ((wg >> 1) & 1) ^ 1);                                             \
+      if (wg >= 2) WAITB(B_ACC0FULL + ws, ((wg >> 1) - 1) & 1);                               \
       mbar_arrive_expect_tx(&bars[B_W0FULL + ws], p.w0g_bytes);                               \
       bulk_g2s_hint(sW0g + ws * p.w0g_bytes,                                                  \
                     wm + p.off_w0g + static_cast<size_t>(wg % NG) * p.w0g_bytes, p.w0g_bytes, \
@@ -525,8 +526,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           if (elect_one()) {
             for (int j = 0; j < k0steps; ++j)
               umma_ts(acc0, ztm + j * 8, w0desc0 + (gg & 1) * w0slot + j * w0_kstep, idesc0, j > 0);
-            umma_commit(&bars[B_ACC0FULL]);
-            umma_commit(&bars[B_W0EMPTY + (gg & 1)]);
+            umma_commit(&bars[B_ACC0FULL + (gg & 1)]);
           }
           __syncwarp();
           ++gg;
@@ -550,8 +550,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               if (next_l0) {
                 for (int j = 0; j < k0steps; ++j)
                   umma_ts(acc0, ztm + j * 8, w0desc0 + (gg & 1) * w0slot + j * w0_kstep, idesc0, j > 0);
-                umma_commit(&bars[B_ACC0FULL]);
-                umma_commit(&bars[B_W0EMPTY + (gg & 1)]);
+                umma_commit(&bars[B_ACC0FULL + (gg & 1)]);
               }
               const uint32_t at = tmem + TM_H0;
               const uint64_t bd = stdesc0 + s * ststride;
@@ -560,7 +559,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               umma_ts(acc1, at + 16, bd + 4, idesc1, 1);
               umma_ts(acc1, at + 24, bd + 6, idesc1, 1);
               umma_commit(&bars[B_EMPTY + s]);
-              umma_commit(&bars[B_H0FREE + 0]);
             }
             __syncwarp();
             if (next_l0) ++gg;
@@ -590,7 +588,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               umma_ts(acc1, at + 16, bd + 4, idesc1, 1);
               umma_ts(acc1, at + 24, bd + 6, idesc1, 1);
               umma_commit(&bars[B_EMPTY + s1]);
-              umma_commit(&bars[B_H0FREE + 1]);
               if (last_of_pass) umma_commit(&bars[B_ACC1FULL]);
             }
             __syncwarp();
@@ -658,13 +655,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
       for (int s = 0; s < SMAX; ++s) x[s] = 0.f;
       int ts = 0, nreset = 0;
       int est = 0;   // steps done by this CTA (trace window index, same as the MMA warp's st)
+      float ep[AMAX];          // N(0,1) policy noise of the upcoming step
+      bool ep_valid = false;
+      int row = 0;
+      bool valid = false;
+      auto load_eps = [&](int tt) {
+        if (p.eps != nullptr) {
+#pragma unroll
+          for (int i = 0; i < AMAX; ++i)
+            ep[i] = (valid && i < A) ? p.eps[(static_cast<size_t>(tt) * p.B + row) * A + i] : 0.f;
+        } else {
+#pragma unroll
+          for (int blk = 0; blk < AMAX / 4; ++blk) {
+            float n4[4];
+            if (blk * 4 < A)
+              philox_normal4(p.seed, static_cast<uint32_t>(p.offset + tt), static_cast<uint32_t>(row),
+                             PHILOX_STREAM_EPS + blk, n4);
+            else
+              n4[0] = n4[1] = n4[2] = n4[3] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ep[blk * 4 + q] = n4[q];
+          }
+        }
+        ep_valid = true;
+      };
 
       for (int si = 0; si < MAX_SEG; ++si) {
         const int4 sg = segs[si];
         if (sg.x < 0) continue;
         const int tile = sg.x, t0 = sg.y, t1 = sg.z;
-        const int row = tile * TILE_M + r;
-        const bool valid = row < p.B;
+        row = tile * TILE_M + r;
+        valid = row < p.B;
+        ep_valid = false;
 
         // ---- segment start: acquire the tile's state ----
         if (sg.w) {
@@ -721,24 +743,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
 #pragma unroll
               for (int i = 0; i < AMAX; ++i) a_raw[i] = a_mean[i];
             } else {
-              float ep[AMAX];
-              if (p.eps != nullptr) {
-#pragma unroll
-                for (int i = 0; i < AMAX; ++i)
-                  ep[i] = (valid && i < A) ? p.eps[(static_cast<size_t>(t) * p.B + row) * A + i] : 0.f;
-              } else {
-#pragma unroll
-                for (int blk = 0; blk < AMAX / 4; ++blk) {
-                  float n4[4];
-                  if (blk * 4 < A)
-                    philox_normal4(p.seed, static_cast<uint32_t>(p.offset + t),
-                                   static_cast<uint32_t>(row), PHILOX_STREAM_EPS + blk, n4);
-                  else
-                    n4[0] = n4[1] = n4[2] = n4[3] = 0.f;
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) ep[blk * 4 + q] = n4[q];
-                }
-              }
+              if (!ep_valid) load_eps(t);      // normally prefetched while waiting for the exchange
+              ep_valid = false;
 #pragma unroll
               for (int i = 0; i < AMAX; ++i) {
                 const float ls = fmaxf(sPol[p.pol_logstd_off + i], -13.815510557964274f);
@@ -784,7 +790,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               {
                 uint32_t v0[32], v1[32], v2[32], v3[32], pk[32], pk2[32];
                 TRACE(2, 0x100 | (2 * G));
-                WAITB(B_ACC0FULL, gg & 1);
+                WAITB(B_ACC0FULL + (gg & 1), (gg >> 1) & 1);
                 TRACE(2, 0x200 | (2 * G));
                 tc_fence_after();
                 tmem_ld32(tmem + lane_base + TM_ACC0, v0);
@@ -797,13 +803,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                 TRACE(2, 0x300 | (2 * G));
                 relu_pack<false>(v0, v1, nullptr, pk);
                 relu_pack<false>(v2, v3, nullptr, pk2);
-                WAITB(B_H0FREE + 0, (gg & 1) ^ 1);
+                // H0 buffer 0 is free once L1 of chunk 2*gg-2 completed (its stage's EMPTY barrier)
+                if (gg >= 1) WAITB(B_EMPTY + ((2 * gg - 2) & 3), ((2 * gg - 2) >> 2) & 1);
                 tmem_st32(tmem + lane_base + TM_H0, pk);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[B_H0FULL + 0]);
                 TRACE(2, 0x400 | (2 * G));
-                WAITB(B_H0FREE + 1, (gg & 1) ^ 1);
+                if (gg >= 1) WAITB(B_EMPTY + ((2 * gg - 1) & 3), ((2 * gg - 1) >> 2) & 1);
                 tmem_st32(tmem + lane_base + TM_H0 + 32, pk2);
                 tmem_st_wait();
                 tc_fence_before();
@@ -870,6 +877,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
             for (int s = 0; s < SMAX; ++s)
               if (s < S) xb[(k * S + s) * TILE_M + r] = cand[s];
             TRACE(2, 0x1020);
+            // useful work while the candidate stores drain and the peers catch up: the parts of
+            // the trajectory record that are already known, and the next step's policy noise
+            if (k == 0 && valid) {
+              const size_t o = static_cast<size_t>(t) * p.B + row;
+              if (p.obs) {
+#pragma unroll
+                for (int s = 0; s < SMAX; ++s)
+                  if (s < S) p.obs[o * S + s] = x[s];
+              }
+#pragma unroll
+              for (int i = 0; i < AMAX; ++i)
+                if (i < A) {
+                  if (p.act) p.act[o * A + i] = a_raw[i];
+                  if (p.mean) p.mean[o * A + i] = a_mean[i];
+                }
+            }
+            if (!p.determ && p.ext_actions == nullptr && t + 1 < t1) load_eps(t + 1);
             // CTA barrier orders the 128 threads' stores before thread 0's gpu-scope release
             named_bar_sync(1, EPI_THREADS);
             TRACE(2, 0x1021);
@@ -959,17 +983,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           const bool dn = env_is_done(p.env_id, S, xnext) || (ts >= p.T_max);   // :603-604
           if (k == 0 && valid) {
             const size_t o = static_cast<size_t>(t) * p.B + row;
-            if (p.obs) {
+            if (K == 1) {   // (with K > 1 these were stored while waiting for the exchange)
+              if (p.obs) {
 #pragma unroll
-              for (int s = 0; s < SMAX; ++s)
-                if (s < S) p.obs[o * S + s] = x[s];
-            }
-#pragma unroll
-            for (int i = 0; i < AMAX; ++i)
-              if (i < A) {
-                if (p.act) p.act[o * A + i] = a_raw[i];
-                if (p.mean) p.mean[o * A + i] = a_mean[i];
+                for (int s = 0; s < SMAX; ++s)
+                  if (s < S) p.obs[o * S + s] = x[s];
               }
+#pragma unroll
+              for (int i = 0; i < AMAX; ++i)
+                if (i < A) {
+                  if (p.act) p.act[o * A + i] = a_raw[i];
+                  if (p.mean) p.mean[o * A + i] = a_mean[i];
+                }
+            }
             if (p.rew) p.rew[o] = reward;
             if (p.done) p.done[o] = dn ? 1 : 0;
           }
