@@ -76,6 +76,8 @@ typedef struct {
   int32_t policy_out_tanh;  /* policy output_nonlinearity: 0 tf.identity, 1 tf.tanh */
   int32_t precision;        /* METRPO_PREC_* */
   int32_t device;           /* CUDA device ordinal */
+  int32_t row_offset;       /* global index of row 0 (Philox streams are keyed by global row, so a
+                               row-sharded multi-GPU run reproduces the single-GPU one) */
 } metrpo_rollout_cfg;
 
 typedef struct metrpo_rollout metrpo_rollout_t;
@@ -166,6 +168,11 @@ int metrpo_rollout_last_launches(const metrpo_rollout_t* h);
  * clock64 span of `reps` back-to-back K loops. */
 int metrpo_selftest_umma(int mode, int N, int K, int reps, const void* A_bf16, const void* B_bf16,
                          float* C, unsigned long long* cycles, void* stream);
+
+/* Host-only helper (no CUDA call): the gang schedule the library builds for n_tiles row tiles of
+ * 128 rows on n_slots gang slots over T steps; out receives n_slots * max_seg quadruples
+ * (tile, t0, t1, wait_flag), tile == -1 for unused entries.  Returns max_seg (> 0) or a status. */
+int metrpo_debug_schedule(int n_tiles, int n_slots, int T, int32_t* out, int out_capacity_quads);
 
 /* Dev tool: tensor-pipe micro-benchmark.  Issues reps x 4 tcgen05.mma (M=128, K=16, given N) from
  * a warp-uniform loop; out_dev[0] = clock64 span of the issue loop, out_dev[1] = span until the

@@ -327,9 +327,7 @@ extern "C" int metrpo_rollout_reset(metrpo_rollout_t* h, const float* states, vo
 // the slot that owns the tail runs it LAST and waits on the tile flag (always already set in
 // practice: per >= T).  Heads never wait, so the schedule cannot deadlock.
 // ---------------------------------------------------------------------------------------------
-static int build_schedule(metrpo_rollout* h, int T, std::vector<int4>& segs, int& n_slots) {
-  const int n_tiles = h->n_tiles;
-  n_slots = h->max_slots;
+static int build_schedule_raw(int n_tiles, int n_slots, int T, std::vector<int4>& segs) {
   const long long total = static_cast<long long>(n_tiles) * T;
   const long long per = (total + n_slots - 1) / n_slots;
   segs.assign(static_cast<size_t>(n_slots) * MAX_SEG, make_int4(-1, 0, 0, 0));
@@ -354,6 +352,24 @@ static int build_schedule(metrpo_rollout* h, int T, std::vector<int4>& segs, int
     for (size_t i = 0; i < order.size(); ++i) segs[static_cast<size_t>(j) * MAX_SEG + i] = order[i];
   }
   return 0;
+}
+static int build_schedule(metrpo_rollout* h, int T, std::vector<int4>& segs, int& n_slots) {
+  n_slots = h->max_slots;
+  return build_schedule_raw(h->n_tiles, n_slots, T, segs);
+}
+
+// Host-only helper (no CUDA): the gang schedule for n_tiles row tiles on n_slots gang slots and a
+// horizon of T steps.  out receives n_slots * max_seg int32 quadruples (tile, t0, t1, wait);
+// tile == -1 marks unused entries.  Returns max_seg, or a negative status.
+extern "C" int metrpo_debug_schedule(int n_tiles, int n_slots, int T, int32_t* out, int out_capacity_quads) {
+  if (n_tiles < 1 || n_slots < 1 || T < 1 || !out) return set_error(METRPO_ERR_INVALID, "debug_schedule: bad argument");
+  if (n_slots > n_tiles) return set_error(METRPO_ERR_INVALID, "debug_schedule: n_slots must be <= n_tiles");
+  if (out_capacity_quads < n_slots * MAX_SEG) return set_error(METRPO_ERR_INVALID, "debug_schedule: output too small (need %d quads)", n_slots * MAX_SEG);
+  std::vector<int4> segs;
+  if (build_schedule_raw(n_tiles, n_slots, T, segs) != 0)
+    return set_error(METRPO_ERR_UNSUPPORTED, "debug_schedule: more than %d segments per slot", MAX_SEG);
+  std::memcpy(out, segs.data(), segs.size() * sizeof(int4));
+  return MAX_SEG;
 }
 
 static int get_schedule(metrpo_rollout* h, int T, const int4** dev, int* n_slots, cudaStream_t st) {
@@ -387,7 +403,7 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
   p.S = c.state_dim; p.A = c.action_dim; p.SA = p.S + p.A; p.drop = c.drop_cols; p.Din = h->Din;
   p.K0 = h->K0; p.H = c.hidden; p.S_pad = h->S_pad; p.K = c.n_models; p.B = c.n_envs;
   p.T_max = c.max_path_length; p.env_id = c.env_id; p.sam_mode = c.sam_mode;
-  p.NC = h->NC; p.KC = h->KC; p.n_tiles = h->n_tiles;
+  p.NC = h->NC; p.KC = h->KC; p.n_tiles = h->n_tiles; p.row_offset = c.row_offset;
   p.wstream = h->wstream; p.model_stride = h->model_stride; p.stage_bytes = h->stage_bytes;
   p.w0g_bytes = h->w0g_bytes; p.w2chunk_bytes = h->w2chunk_bytes; p.off_w2 = h->off_w2;
   p.off_w0g = h->off_w0g; p.bias = h->bias; p.norm = h->norm; p.pol = h->pol;

@@ -96,6 +96,7 @@ struct KParams {
   int NC, KC;
   int n_steps, n_slots, n_tiles;
   int resume;            // 1: state comes from row_state (B1 step / continued run)
+  int row_offset;        // global index of local row 0 (keys the Philox streams)
   // packed weights (per model: W1 stages | W2 chunks | W0 group tiles)
   const uint8_t* wstream;
   unsigned long long model_stride;
@@ -669,7 +670,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           for (int blk = 0; blk < AMAX / 4; ++blk) {
             float n4[4];
             if (blk * 4 < A)
-              philox_normal4(p.seed, static_cast<uint32_t>(p.offset + tt), static_cast<uint32_t>(row),
+              philox_normal4(p.seed, static_cast<uint32_t>(p.offset + tt), static_cast<uint32_t>(row + p.row_offset),
                              PHILOX_STREAM_EPS + blk, n4);
             else
               n4[0] = n4[1] = n4[2] = n4[3] = 0.f;
@@ -917,10 +918,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                   idx = valid ? p.model_idx[static_cast<size_t>(t) * p.B + row] : 0;
                 else if (mode == METRPO_SAM_STEP_RAND)
                   idx = philox_index(p.seed, static_cast<uint32_t>(p.offset + t),
-                                     static_cast<uint32_t>(row), PHILOX_STREAM_IDX, K);
+                                     static_cast<uint32_t>(row + p.row_offset), PHILOX_STREAM_IDX, K);
                 else
                   idx = philox_index(p.seed, static_cast<uint32_t>(nreset),
-                                     static_cast<uint32_t>(row), PHILOX_STREAM_EIDX, K);
+                                     static_cast<uint32_t>(row + p.row_offset), PHILOX_STREAM_EIDX, K);
                 idx = min(max(idx, 0), K - 1);
               }
 #pragma unroll
@@ -946,7 +947,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                   } else {
                     float n4[4];
                     philox_normal4(p.seed, static_cast<uint32_t>(p.offset + t),
-                                   static_cast<uint32_t>(row), PHILOX_STREAM_STD + (s >> 2), n4);
+                                   static_cast<uint32_t>(row + p.row_offset), PHILOX_STREAM_STD + (s >> 2), n4);
                     nz = n4[s & 3];
                   }
                   outv = __fadd_rn(m, __fmul_rn(nz, sd));

@@ -32,7 +32,7 @@ class RolloutCfg(ctypes.Structure):
         ("sam_mode", ctypes.c_int32), ("n_policy_layers", ctypes.c_int32),
         ("policy_dims", ctypes.c_int32 * (MAX_POLICY_LAYERS + 1)),
         ("policy_out_tanh", ctypes.c_int32), ("precision", ctypes.c_int32),
-        ("device", ctypes.c_int32),
+        ("device", ctypes.c_int32), ("row_offset", ctypes.c_int32),
     ]
 
 
@@ -53,6 +53,7 @@ _PROTOS = {
     "metrpo_rollout_status": (_i, [_vp, _vp]),
     "metrpo_rollout_set_trace": (_i, [_vp, _i, _i, _i]),
     "metrpo_rollout_get_trace": (_i, [_vp, _vp]),
+    "metrpo_debug_schedule": (_i, [_i, _i, _i, _vp, _i]),
     "metrpo_bench_mma": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "metrpo_selftest_umma": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -22,7 +22,7 @@ class EnsembleRollout:
 
     def __init__(self, env, n_models, n_envs, max_path_length, hidden=None, policy_hidden=None,
                  sam_mode="step_rand", drop_cols=None, policy_out_tanh=False, device=None,
-                 state_dim=None, action_dim=None):
+                 state_dim=None, action_dim=None, row_offset=0):
         name = canonical_env_name(env)
         spec = ENV_SPECS[name]
         self.env_name = name
@@ -53,6 +53,7 @@ class EnsembleRollout:
             cfg.policy_dims[i] = d
         cfg.policy_out_tanh = 1 if policy_out_tanh else 0
         cfg.precision = 0
+        cfg.row_offset = int(row_offset)
         cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._h = ctypes.c_void_p()
         _lib.check(self._lib.metrpo_rollout_create(ctypes.byref(cfg), ctypes.byref(self._h)),

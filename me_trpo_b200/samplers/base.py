@@ -1,0 +1,45 @@
+"""BaseSampler.process_samples (samplers/base.py:48-182) for the non-recurrent case: baseline
+prediction, TD residuals, discounted cumulative sums, advantage centring, baseline refit.
+
+Host (NumPy) implementation operating on the list-of-paths format of socket B2; the on-device
+version for flat trajectory buffers is the N1 row of SURVEY.md 8(f)."""
+import numpy as np
+
+
+def discount_cumsum(x, discount):
+    """y_t = x_t + discount * y_{t+1} (rllab special.discount_cumsum)."""
+    y = np.zeros(len(x), dtype=np.float64)
+    run = 0.0
+    for t in range(len(x) - 1, -1, -1):
+        run = x[t] + discount * run
+        y[t] = run
+    return y
+
+
+class BaseSampler:
+    def __init__(self, algo):
+        self.algo = algo
+
+    def process_samples(self, itr, paths):
+        algo = self.algo
+        gamma, lam = algo.discount, algo.gae_lambda
+        path_baselines = [algo.baseline.predict(p) for p in paths]
+        for p, b in zip(paths, path_baselines):
+            b1 = np.append(b, 0.0)
+            deltas = p["rewards"] + gamma * b1[1:] - b1[:-1]
+            p["advantages"] = discount_cumsum(deltas, gamma * lam)
+            p["returns"] = discount_cumsum(p["rewards"], gamma)
+        cat = lambda key: np.concatenate([p[key] for p in paths])
+        advantages = cat("advantages")
+        if algo.center_adv:
+            advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)
+        if getattr(algo, "positive_adv", False):
+            advantages = advantages - advantages.min() + 1e-8
+        samples_data = dict(
+            observations=cat("observations"), actions=cat("actions"), rewards=cat("rewards"),
+            returns=cat("returns"), advantages=advantages, env_infos={},
+            agent_infos={k: np.concatenate([p["agent_infos"][k] for p in paths])
+                         for k in paths[0]["agent_infos"]},
+            paths=paths)
+        algo.baseline.fit(paths)   # after the advantages: iteration j uses the fit of j-1
+        return samples_data

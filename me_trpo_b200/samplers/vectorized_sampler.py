@@ -1,0 +1,93 @@
+"""VectorizedSampler (samplers/vectorized_sampler.py): socket B2.
+
+`obtain_samples` keeps the reference's contract -- a list of COMPLETED path dicts with
+observations (pre-step), UNCLIPPED actions, rewards, agent_infos{mean, log_std} -- but produces it
+with ONE persistent kernel launch for the whole batch instead of a Python loop with two session
+round trips per env-step.  `obtain_samples_flat` returns the time-major device buffers directly
+(what an on-device policy update consumes)."""
+import numpy as np
+import torch
+
+from .base import BaseSampler
+from ..rollout import EnsembleRollout
+
+
+class VectorizedSampler(BaseSampler):
+    def __init__(self, algo, n_envs=None, seed=0, reset_pool_size=None):
+        super().__init__(algo)
+        self.n_envs = n_envs
+        self.seed = int(seed)
+        self.reset_pool_size = reset_pool_size
+        self.rollout = None
+        self._calls = 0
+
+    def start_worker(self):
+        algo = self.algo
+        n_envs = self.n_envs
+        if n_envs is None:   # reference rule (:26-27); pass n_envs explicitly to use the whole GPU
+            n_envs = max(1, min(int(algo.batch_size / algo.max_path_length), 100))
+        env = algo.env
+        if not getattr(env, "vectorized", False):
+            raise RuntimeError("VectorizedSampler needs a vectorized (NeuralNetEnv) environment")
+        pol = algo.policy
+        self.rollout = EnsembleRollout(env.env_name, env.n_models, n_envs, algo.max_path_length,
+                                       hidden=env.hidden, policy_hidden=pol.hidden_sizes,
+                                       sam_mode=env.sam_mode, policy_out_tanh=pol.output_tanh,
+                                       device=env.device)
+        self.rollout.set_dynamics_ensemble(env.models)
+        self.rollout.set_normalization(**env.norm)
+        self.env_spec = env.spec
+        self._n_envs = n_envs
+
+    def shutdown_worker(self):
+        if self.rollout is not None:
+            self.rollout.close()
+            self.rollout = None
+
+    def _steps_for_batch(self):
+        """Number of kernel steps so that completed paths cover batch_size samples: with a common
+        timeout every row completes a path each max_path_length steps (:60 loops until then)."""
+        algo = self.algo
+        per_round = self._n_envs * algo.max_path_length
+        rounds = -(-int(algo.batch_size) // per_round)
+        return rounds * algo.max_path_length
+
+    def obtain_samples_flat(self, itr, determ=False, n_steps=None):
+        algo, env, pol = self.algo, self.algo.env, self.algo.policy
+        B = self._n_envs
+        T = int(n_steps or self._steps_for_batch())
+        self.rollout.set_policy(pol.W, pol.b, pol.log_std)
+        n_resets = -(-T // algo.max_path_length)
+        R = int(self.reset_pool_size or B * n_resets)
+        init = np.asarray(env.reset_sampler(B), np.float32)          # the initial reset() (:49)
+        pool = np.asarray(env.reset_sampler(R), np.float32)
+        out = self.rollout.run(T, init, pool, seed=self.seed, offset=self._calls * (1 << 20),
+                               determ=determ)
+        self._calls += 1
+        return out
+
+    def obtain_samples(self, itr, determ=False):
+        flat = self.obtain_samples_flat(itr, determ)
+        self.rollout.synchronize()
+        log_std = self.algo.policy.log_std.clamp(min=float(np.log(1e-6))).cpu().numpy()
+        host = {k: v.cpu().numpy() for k, v in flat.items()}
+        return paths_from_flat(host, log_std)
+
+
+def paths_from_flat(flat, log_std):
+    """Cut time-major buffers [T,B,...] into the reference's list of completed path dicts, in the
+    order the reference appends them (by finishing step, then row)."""
+    T, B = flat["rew"].shape
+    done = flat["done"].astype(bool)
+    start = np.zeros(B, np.int64)
+    paths = []
+    for t in np.nonzero(done.any(axis=1))[0]:
+        for b in np.nonzero(done[t])[0]:
+            sl = slice(start[b], t + 1)
+            L = t + 1 - start[b]
+            paths.append(dict(
+                observations=flat["obs"][sl, b], actions=flat["act"][sl, b], rewards=flat["rew"][sl, b],
+                env_infos={}, agent_infos=dict(mean=flat["mean"][sl, b],
+                                               log_std=np.tile(log_std, (L, 1)))))
+            start[b] = t + 1
+    return paths

@@ -226,7 +226,7 @@ class VecSimpleEnvOracle:
 def get_actions(pol, obses, eps, dtype=np.float32, out_tanh=False):
     """rllab GaussianMLPPolicy.get_actions: actions = rnd*exp(log_std) + mean."""
     mean = _models.policy_forward(pol, obses, dtype, out_tanh)
-    log_std = np.maximum(pol["log_std"].astype(dtype), np.log(1e-6))     # min_std clamp
+    log_std = np.maximum(pol["log_std"].astype(dtype), dtype(np.log(1e-6)))   # min_std clamp
     log_std = np.broadcast_to(log_std, mean.shape)
     actions = eps.astype(dtype) * np.exp(log_std) + mean
     return actions, dict(mean=mean, log_std=log_std)
