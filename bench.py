@@ -39,16 +39,10 @@ def flops_per_step(spec, K, B, T, hidden):
 
 def make_problem(seed=0, B=B_ROWS):
     """Synthetic weights / states of the BASELINE shape: Xavier-uniform nets with the
-    dynamics output layer scaled by 0.1 so that a 1000-step rollout of a random net stays finite."""
-    from oracle import envs as oe, models as om
-    spec = oe.ENV_SPECS[ENV]
-    rng = np.random.RandomState(seed)
-    models = om.init_dynamics(rng, spec["S"], spec["A"], spec["drop"], HIDDEN, K_MODELS)
-    pol = om.init_policy(rng, spec["S"], spec["policy_hidden"], spec["A"])
-    norm = om.default_norm(spec["S"], spec["A"])
-    init = rng.normal(0, 0.1, (B, spec["S"])).astype(np.float32)
-    pool = rng.normal(0, 0.1, (B, spec["S"])).astype(np.float32)
-    return spec, models, pol, norm, init, pool
+    dynamics output layer scaled by 0.1 so that a 1000-step rollout of a random net stays finite.
+    Product-side generator (me_trpo_b200/synthetic.py): the CUDA arm never imports oracle/."""
+    from me_trpo_b200 import synthetic
+    return synthetic.make_problem(ENV, K_MODELS, B, hidden=HIDDEN, seed=seed)
 
 
 class ClockSampler(threading.Thread):
