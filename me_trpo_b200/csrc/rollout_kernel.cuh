@@ -598,22 +598,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               // The next pass's L1 overwrites acc1 only after these MMAs (same issuing thread,
               // in-order pipe), so no "acc1 free" barrier is needed.
               TRACE(1, 0x2000 | nc);
-              // all four 64-column slices must be converted; one wait round, one MMA batch
-              WAITW4(B_H1FULL + 0, npass & 1, B_H1FULL + 1, npass & 1, B_H1FULL + 2, npass & 1,
-                     B_H1FULL + 3, npass & 1);
-              WAITW1(B_W2FULL, w2n & 1); ++w2n;
+              // each 64-column slice is consumed as soon as the epilogue has converted it, so the
+              // L2 MMAs of slice s overlap the conversion of slice s+1
+              WAITW2(B_H1FULL + 0, npass & 1, B_W2FULL, w2n & 1); ++w2n;
               TRACE(1, 0x2200 | (nc << 4));
-              tc_fence_after();
-              if (elect_one()) {
-#pragma unroll
-                for (int sub = 0; sub < 4; ++sub) {
+#pragma unroll 1
+              for (int sub = 0; sub < 4; ++sub) {
+                if (sub > 0) WAITW1(B_H1FULL + sub, npass & 1);
+                tc_fence_after();
+                if (elect_one()) {
                   const uint32_t at = acc1 + sub * 64;
                   const uint64_t bd = w2desc + sub * w2_sub;
 #pragma unroll
                   for (int j = 0; j < 4; ++j) umma_ts(acc2, at + 8 * j, bd + 2 * j, idesc2, (nc | sub | j) != 0);
                 }
+                __syncwarp();
               }
-              __syncwarp();
               TRACE(1, 0x2400 | (nc << 4));
               if (elect_one()) umma_commit(&bars[B_W2EMPTY]);
               __syncwarp();
@@ -831,18 +831,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                 WAITB(B_ACC1FULL, a1n & 1);
                 TRACE(2, 0x800 | (2 * G));
                 tc_fence_after();
-#pragma unroll 1
-                for (int sub = 0; sub < 4; ++sub) {
-                  uint32_t v0[32], v1[32], pk[32];
-                  tmem_ld32(tmem + lane_base + TM_ACC1 + sub * 64, v0);
-                  tmem_ld32(tmem + lane_base + TM_ACC1 + sub * 64 + 32, v1);
+                {
+                  // software pipelined: the TMEM loads of slice s+1 are in flight while slice s is
+                  // converted and stored (slices touch disjoint columns)
+                  uint32_t va0[32], va1[32], vb0[32], vb1[32], pk[32];
+                  const uint32_t a1 = tmem + lane_base + TM_ACC1;
+                  const float* bb = sB1 + drain_nc * 256;
+                  tmem_ld32(a1, va0);
+                  tmem_ld32(a1 + 32, va1);
                   tmem_ld_wait();
-                  relu_pack<true>(v0, v1, sB1 + drain_nc * 256 + sub * 64, pk);
-                  // in place: the 64 fp32 columns just read become 32 columns of bf16 pairs
-                  tmem_st32(tmem + lane_base + TM_ACC1 + sub * 64, pk);
-                  tmem_st_wait();
-                  tc_fence_before();
-                  mbar_arrive(&bars[B_H1FULL + sub]);
+#define DRAIN_SLICE(sub, cur0, cur1, nxt0, nxt1, has_next)                                    \
+                  if (has_next) {                                                             \
+                    tmem_ld32(a1 + ((sub) + 1) * 64, nxt0);                                   \
+                    tmem_ld32(a1 + ((sub) + 1) * 64 + 32, nxt1);                              \
+                  }                                                                           \
+                  relu_pack<true>(cur0, cur1, bb + (sub) * 64, pk);                           \
+                  /* in place: the 64 fp32 columns just read become 32 columns of bf16 pairs */ \
+                  tmem_st32(a1 + (sub) * 64, pk);                                             \
+                  tmem_st_wait();                                                             \
+                  tc_fence_before();                                                          \
+                  mbar_arrive(&bars[B_H1FULL + (sub)]);                                       \
+                  if (has_next) tmem_ld_wait();
+                  DRAIN_SLICE(0, va0, va1, vb0, vb1, true)
+                  DRAIN_SLICE(1, vb0, vb1, va0, va1, true)
+                  DRAIN_SLICE(2, va0, va1, vb0, vb1, true)
+                  DRAIN_SLICE(3, vb0, vb1, va0, va1, false)
+#undef DRAIN_SLICE
                 }
                 ++a1n;
                 TRACE(2, 0x900 | (2 * G));
