@@ -180,6 +180,83 @@ int metrpo_debug_schedule(int n_tiles, int n_slots, int T, int32_t* out, int out
 int metrpo_bench_mma(int ts_mode, int N, int reps, int two_acc, int a_col, int d_col,
                      int wait_each, unsigned long long* out_dev, void* stream);
 
+/* =============================================================================================
+ * TRPO half of the inner iteration: sample processing + natural-gradient policy update.
+ * All buffers are DEVICE pointers unless marked host; sample index n = t * B + b (the time-major
+ * layout metrpo_rollout_run writes), so the trajectory buffers are consumed in place.
+ * ============================================================================================= */
+typedef struct {
+  int32_t state_dim;        /* S */
+  int32_t action_dim;       /* A (<= 24) */
+  int32_t n_policy_layers;  /* weight matrices of the mean network (training.py:96-103) */
+  int32_t policy_dims[METRPO_MAX_POLICY_LAYERS + 1]; /* S, h1, .., A */
+  int32_t policy_out_tanh;  /* output_nonlinearity: 0 identity, 1 tanh (training.py:82) */
+  int32_t device;
+} metrpo_trpo_cfg;
+
+typedef struct metrpo_trpo metrpo_trpo_t;
+
+/* Cross-rank SUM of n doubles at dev_buf, in place, ordered on `stream` (e.g. an NCCL all-reduce
+ * issued by the host framework).  Returns 0 on success.  Without a callback the update is
+ * single-GPU.  Every reduction is <= P + 4 doubles (latency-bound collectives). */
+typedef int (*metrpo_allreduce_fn)(void* user, double* dev_buf, int n, void* stream);
+
+int metrpo_trpo_create(const metrpo_trpo_cfg* cfg, metrpo_trpo_t** out);
+int metrpo_trpo_destroy(metrpo_trpo_t* h);
+int metrpo_trpo_set_allreduce(metrpo_trpo_t* h, metrpo_allreduce_fn fn, void* user);
+/* length P of the flat parameter vector, rllab get_params(trainable=True) order:
+ * W0[in,out], b0, W1, b1, .., log_std[A]   */
+int metrpo_trpo_num_params(const metrpo_trpo_t* h);
+int metrpo_trpo_last_launches(const metrpo_trpo_t* h);
+
+/* BaseSampler.process_samples (samplers/base.py:48-105) on flat buffers obs[T,B,S], rew[T,B],
+ * done[T,B]: baseline prediction (coeffs [2S+4] doubles, NULL = not fitted yet -> zeros,
+ * :55), deltas (:57-59), advantages = discount_cumsum(deltas, discount*gae_lambda) (:60-61),
+ * returns (:62), center_advantages (:82-83), shift_advantages_to_positive (:85-86).
+ * Samples of paths still open at the end of the buffer get valid = 0 and adv = ret = 0
+ * (obtain_samples returns completed paths only, samplers/vectorized_sampler.py:80-105).
+ * stats (8 doubles): n_valid, sum, sum of squares, min, mean, std of the raw advantages. */
+int metrpo_trpo_process(metrpo_trpo_t* h, int T, int B, const float* obs, const float* rew,
+                        const uint8_t* done, const double* baseline_coeffs, double discount,
+                        double gae_lambda, int center_adv, int positive_adv, float* adv, float* ret,
+                        uint8_t* valid, double* stats, void* stream);
+
+/* rllab LinearFeatureBaseline.fit (samplers/base.py:167): ridge regression of the
+ * returns on [o, o^2, t/100, (t/100)^2, (t/100)^3, 1], o = clip(obs,-10,10), t = index in path;
+ * coeffs_out [2S+4] doubles; reg retried x10 up to 5 times while the solution has NaNs. */
+int metrpo_trpo_fit_baseline(metrpo_trpo_t* h, int T, int B, const float* obs, const float* ret,
+                             const uint8_t* valid, const uint8_t* done, double reg_coeff,
+                             double* coeffs_out, void* stream);
+
+/* NPO.optimize_policy -> ConjugateGradientOptimizer.optimize (algos/npo.py:94-111)
+ * over N samples: obs[N,S], act[N,A] (unclipped actions), adv[N], old_mean[N,A], old_log_std
+ * ([A], or [N,A] when old_log_std_per_sample), valid[N] or NULL.  theta [P] floats is updated in
+ * place: loss_before, flat gradient, cg_iters CG iterations on Hx = Fisher-vector product +
+ * reg_coeff x, step = sqrt(2 step_size / (d.Hd + 1e-8)), back-tracking over
+ * backtrack_ratio ** arange(max_backtracks) accepting the first trial with loss < loss_before and
+ * mean_kl <= step_size, else the previous parameters are restored.  No host synchronisation.
+ * info (8 doubles, may be NULL): loss_before, loss_after, mean_kl, backtrack index, accepted,
+ * initial step, n_valid, d.Hd. */
+int metrpo_trpo_update(metrpo_trpo_t* h, long long N, const float* obs, const float* act,
+                       const float* adv, const float* old_mean, const float* old_log_std,
+                       int old_log_std_per_sample, const uint8_t* valid, float* theta,
+                       double step_size, int cg_iters, double reg_coeff, double backtrack_ratio,
+                       int max_backtracks, double* info, void* stream);
+
+/* optimizer.loss / optimizer.constraint_val (algos/npo.py:108-114): out2 (HOST, 2 doubles) =
+ * (surr_loss, mean_kl) at theta.  Synchronises the stream. */
+int metrpo_trpo_loss_kl(metrpo_trpo_t* h, long long N, const float* obs, const float* act,
+                        const float* adv, const float* old_mean, const float* old_log_std,
+                        int old_log_std_per_sample, const uint8_t* valid, const float* theta,
+                        double* out2, void* stream);
+
+/* Test hook: vec == NULL -> flat gradient of surr_loss at theta; else Hx(vec) = Fisher-vector
+ * product + reg_coeff * vec.  out_host: P doubles (HOST).  Synchronises the stream. */
+int metrpo_trpo_grad(metrpo_trpo_t* h, long long N, const float* obs, const float* act,
+                     const float* adv, const float* old_mean, const float* old_log_std,
+                     int old_log_std_per_sample, const uint8_t* valid, const float* theta,
+                     const float* vec, double reg_coeff, double* out_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

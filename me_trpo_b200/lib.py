@@ -36,7 +36,18 @@ class RolloutCfg(ctypes.Structure):
     ]
 
 
+class TrpoCfg(ctypes.Structure):
+    _fields_ = [
+        ("state_dim", ctypes.c_int32), ("action_dim", ctypes.c_int32),
+        ("n_policy_layers", ctypes.c_int32),
+        ("policy_dims", ctypes.c_int32 * (MAX_POLICY_LAYERS + 1)),
+        ("policy_out_tanh", ctypes.c_int32), ("device", ctypes.c_int32),
+    ]
+
+
 _vp, _i, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+_ll, _d = ctypes.c_longlong, ctypes.c_double
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
 _PROTOS = {
     "metrpo_version": (ctypes.c_char_p, []),
     "metrpo_last_error": (ctypes.c_char_p, []),
@@ -56,6 +67,16 @@ _PROTOS = {
     "metrpo_debug_schedule": (_i, [_i, _i, _i, _vp, _i]),
     "metrpo_bench_mma": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "metrpo_selftest_umma": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "metrpo_trpo_create": (_i, [ctypes.POINTER(TrpoCfg), ctypes.POINTER(_vp)]),
+    "metrpo_trpo_destroy": (_i, [_vp]),
+    "metrpo_trpo_set_allreduce": (_i, [_vp, ALLREDUCE_FN, _vp]),
+    "metrpo_trpo_num_params": (_i, [_vp]),
+    "metrpo_trpo_last_launches": (_i, [_vp]),
+    "metrpo_trpo_process": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "metrpo_trpo_fit_baseline": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp]),
+    "metrpo_trpo_update": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _d, _i, _d, _d, _i, _vp, _vp]),
+    "metrpo_trpo_loss_kl": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "metrpo_trpo_grad": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _d, _vp, _vp]),
 }
 
 _lib = None

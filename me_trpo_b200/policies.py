@@ -46,6 +46,18 @@ class GaussianMLPPolicy:
             o += n
         assert o == flat.numel()
 
+    def flat_params(self):
+        """Flat fp32 device vector in get_params(trainable=True) order (what the optimizer updates)."""
+        return torch.cat([p.reshape(-1) for p in self.get_params()]).contiguous()
+
+    def set_flat_params(self, flat):
+        o = 0
+        for p in self.get_params():
+            n = p.numel()
+            p.copy_(flat[o:o + n].reshape(p.shape))
+            o += n
+        assert o == flat.numel()
+
     def reset(self, dones=None):
         pass   # feed-forward policy: no state
 

@@ -19,6 +19,38 @@ def discount_cumsum(x, discount):
 class BaseSampler:
     def __init__(self, algo):
         self.algo = algo
+        self._update_kernels = None
+
+    def _kernels(self):
+        if self._update_kernels is None:
+            from ..trpo import PolicyUpdate
+            pol = self.algo.policy
+            dims = [pol.obs_dim] + list(pol.hidden_sizes) + [pol.action_dim]
+            self._update_kernels = PolicyUpdate(dims, out_tanh=pol.output_tanh, device=pol.device)
+        return self._update_kernels
+
+    def process_samples_flat(self, itr, flat):
+        """process_samples (samplers/base.py:48-182) on the time-major DEVICE buffers of
+        `obtain_samples_flat`: no list of paths, no host copy (metrpo_trpo_process +
+        metrpo_trpo_fit_baseline).  Samples of paths left unfinished at the end of the buffer carry
+        valids == 0 (the reference drops those paths, samplers/vectorized_sampler.py:80-105)."""
+        import torch
+        algo, ku, bl = self.algo, self._kernels(), self.algo.baseline
+        pr = ku.process(flat["obs"], flat["rew"], flat["done"], bl.device_coeffs(ku.device),
+                        discount=algo.discount, gae_lambda=algo.gae_lambda, center_adv=algo.center_adv,
+                        positive_adv=getattr(algo, "positive_adv", False))
+        T, B = flat["rew"].shape
+        N = T * B
+        log_std = torch.clamp(algo.policy.log_std, min=float(np.log(1e-6)))
+        samples_data = dict(
+            observations=flat["obs"].reshape(N, -1), actions=flat["act"].reshape(N, -1),
+            rewards=flat["rew"].reshape(N), returns=pr["ret"].reshape(N), advantages=pr["adv"].reshape(N),
+            valids=pr["valid"].reshape(N), env_infos={},
+            agent_infos=dict(mean=flat["mean"].reshape(N, -1), log_std=log_std), stats=pr["stats"])
+        # after the advantages: iteration j uses the fit of j-1 (:167)
+        bl.set_device_coeffs(ku.fit_baseline(flat["obs"], pr["ret"], pr["valid"], flat["done"],
+                                             reg_coeff=bl._reg_coeff))
+        return samples_data
 
     def process_samples(self, itr, paths):
         algo = self.algo

@@ -30,6 +30,8 @@ class VectorizedSampler(BaseSampler):
         if not getattr(env, "vectorized", False):
             raise RuntimeError("VectorizedSampler needs a vectorized (NeuralNetEnv) environment")
         pol = algo.policy
+        if self.rollout is not None:      # the reference rebuilds the vec env every iteration (:23-40)
+            self.rollout.close()
         self.rollout = EnsembleRollout(env.env_name, env.n_models, n_envs, algo.max_path_length,
                                        hidden=env.hidden, policy_hidden=pol.hidden_sizes,
                                        sam_mode=env.sam_mode, policy_out_tanh=pol.output_tanh,
