@@ -149,6 +149,20 @@ int metrpo_rollout_run(metrpo_rollout_t* h, int n_steps, const float* init_state
                        uint64_t offset, int determ, float* obs, float* act, float* mean,
                        float* rew, uint8_t* done, float* final_states, void* stream);
 
+/* Per-model validation cost of the current policy, the `policy_costs` tensors of
+ * build_policy_graph (model_based_rl.py:122-142) that optimize_policy evaluates every log_every
+ * iterations on the fixed validation initial states (:1237-1248) to feed the stop criterion
+ * (utils.py:285-296).  Each of the K models rolls ITS OWN prediction forward for n_steps steps from
+ * init_states [n_rows,S] (n_rows <= n_envs) under the deterministic, clipped policy (stochastic = 0,
+ * :130); no model selection, no reset, no timeout.  Same persistent kernel as metrpo_rollout_run.
+ *   cost_k = sum_t gamma^t * mean_rows cost_tf(x, u, x')   (Ant: rows that already hit is_done_tf
+ *            contribute 0, envs/com_ant_env.py:70-75,103-117)
+ *   row_costs   [K,n_rows] per-(model,row) discounted sums, or NULL (library workspace)
+ *   model_costs [K] floats. */
+int metrpo_rollout_model_costs(metrpo_rollout_t* h, int n_steps, int n_rows,
+                               const float* init_states, double gamma, float* row_costs,
+                               float* model_costs, void* stream);
+
 /* Synchronise the stream and report the outcome of the last launch: METRPO_OK, or METRPO_ERR_STATE
  * with a message naming the stalled barrier if the kernel's bounded waits timed out (the kernel
  * aborts itself instead of hanging the GPU). */

@@ -71,6 +71,21 @@ __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < npad) dst[i] = i < n ? src[i] : pad;
 }
+// model_costs[k] = mean over rows of row_costs[k][.]  (cost_tf's tf.reduce_mean over the batch,
+// envs/com_*_env.py cost_tf; summed over time per row first, which commutes)
+__global__ void mean_rows_kernel(const float* __restrict__ row_costs, float* __restrict__ out, int n) {
+  __shared__ double sh[256];
+  const float* src = row_costs + static_cast<size_t>(blockIdx.x) * n;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += static_cast<double>(src[i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = static_cast<float>(sh[0] / n);
+}
 __global__ void reset_rows_kernel(const float* __restrict__ states, float* __restrict__ row_state,
                                   int* __restrict__ row_ts, int* __restrict__ row_nreset, int B, int S,
                                   int rows_padded) {
@@ -106,8 +121,9 @@ struct metrpo_rollout {
   unsigned long long* trace = nullptr;
   int trace_cta = 0, trace_t0 = 0, trace_t1 = 0;
   int dbg_words = 0;
-  std::map<int, int4*> schedules;   // n_steps -> device [max_slots][MAX_SEG]
-  std::map<int, int> schedule_slots;
+  std::map<long long, int4*> schedules;   // schedule key -> device [max_slots][MAX_SEG]
+  std::map<long long, int> schedule_slots;
+  float* pm_cost = nullptr;               // [K][n_envs] per-(model,row) validation costs
   // policy blob meta
   PolicyLayer pl[4];
   int pol_floats = 0, pol_logstd_off = 0;
@@ -125,7 +141,7 @@ static void free_handle(metrpo_rollout* h) {
   if (!h) return;
   cudaFree(h->wstream); cudaFree(h->bias); cudaFree(h->norm); cudaFree(h->pol); cudaFree(h->xbuf);
   cudaFree(h->xctr); cudaFree(h->row_state); cudaFree(h->row_ts); cudaFree(h->row_nreset);
-  cudaFree(h->tile_flag); cudaFree(h->dbg); cudaFree(h->trace);
+  cudaFree(h->tile_flag); cudaFree(h->dbg); cudaFree(h->trace); cudaFree(h->pm_cost);
   for (auto& kv : h->schedules) cudaFree(kv.second);
   delete h;
 }
@@ -236,6 +252,7 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   alloc(reinterpret_cast<void**>(&h->row_ts), rows_pad * 4);
   alloc(reinterpret_cast<void**>(&h->row_nreset), rows_pad * 4);
   alloc(reinterpret_cast<void**>(&h->tile_flag), h->n_tiles * 4);
+  alloc(reinterpret_cast<void**>(&h->pm_cost), static_cast<size_t>(c.n_models) * c.n_envs * 4);
   h->dbg_words = DBG_HEADER + h->max_slots * c.n_models * (NUM_THREADS / 32) * DBG_WORDS_PER_WARP;
   alloc(reinterpret_cast<void**>(&h->dbg), h->dbg_words * 4);
   if (e == cudaSuccess)
@@ -372,24 +389,45 @@ extern "C" int metrpo_debug_schedule(int n_tiles, int n_slots, int T, int32_t* o
   return MAX_SEG;
 }
 
-static int get_schedule(metrpo_rollout* h, int T, const int4** dev, int* n_slots, cudaStream_t st) {
-  auto it = h->schedules.find(T);
+// per-model cost rollouts carry per-(model,row) accumulators in registers, so their tile chains are
+// never split: slot j runs tiles j, j + n_slots, .. whole
+static int build_schedule_whole(int n_tiles, int n_slots, int T, std::vector<int4>& segs) {
+  segs.assign(static_cast<size_t>(n_slots) * MAX_SEG, make_int4(-1, 0, 0, 0));
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int j = tile % n_slots, i = tile / n_slots;
+    if (i >= MAX_SEG) return -1;
+    segs[static_cast<size_t>(j) * MAX_SEG + i] = make_int4(tile, 0, T, 0);
+  }
+  return 0;
+}
+
+// whole_tiles > 0: per-model schedule over that many row tiles
+static int get_schedule(metrpo_rollout* h, int T, int whole_tiles, const int4** dev, int* n_slots, cudaStream_t st) {
+  const long long key = (static_cast<long long>(whole_tiles) << 32) | static_cast<unsigned>(T);
+  auto it = h->schedules.find(key);
   if (it != h->schedules.end()) {
     *dev = it->second;
-    *n_slots = h->schedule_slots[T];
+    *n_slots = h->schedule_slots[key];
     return METRPO_OK;
   }
   std::vector<int4> segs;
   int ns = 0;
-  if (build_schedule(h, T, segs, ns) != 0)
+  int brc;
+  if (whole_tiles > 0) {
+    ns = std::min(whole_tiles, h->max_slots);
+    brc = build_schedule_whole(whole_tiles, ns, T, segs);
+  } else {
+    brc = build_schedule(h, T, segs, ns);
+  }
+  if (brc != 0)
     return set_error(METRPO_ERR_UNSUPPORTED, "run: schedule needs more than %d segments per slot (n_tiles=%d, slots=%d)", MAX_SEG, h->n_tiles, h->max_slots);
   int4* d = nullptr;
   METRPO_CUDA_OK(cudaMalloc(&d, segs.size() * sizeof(int4)));
   // one-time synchronous upload (first call with this horizon only)
   METRPO_CUDA_OK(cudaMemcpy(d, segs.data(), segs.size() * sizeof(int4), cudaMemcpyHostToDevice));
   (void)st;
-  h->schedules[T] = d;
-  h->schedule_slots[T] = ns;
+  h->schedules[key] = d;
+  h->schedule_slots[key] = ns;
   *dev = d;
   *n_slots = ns;
   return METRPO_OK;
@@ -401,9 +439,11 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
   if (!h->norm_set) return set_error(METRPO_ERR_STATE, "run: normalization constants were never set");
   const metrpo_rollout_cfg& c = h->cfg;
   p.S = c.state_dim; p.A = c.action_dim; p.SA = p.S + p.A; p.drop = c.drop_cols; p.Din = h->Din;
-  p.K0 = h->K0; p.H = c.hidden; p.S_pad = h->S_pad; p.K = c.n_models; p.B = c.n_envs;
+  p.K0 = h->K0; p.H = c.hidden; p.S_pad = h->S_pad; p.K = c.n_models;
+  if (!p.per_model) p.B = c.n_envs;
   p.T_max = c.max_path_length; p.env_id = c.env_id; p.sam_mode = c.sam_mode;
-  p.NC = h->NC; p.KC = h->KC; p.n_tiles = h->n_tiles; p.row_offset = c.row_offset;
+  p.NC = h->NC; p.KC = h->KC; p.row_offset = c.row_offset;
+  p.n_tiles = p.per_model ? (p.B + TILE_M - 1) / TILE_M : h->n_tiles;
   p.wstream = h->wstream; p.model_stride = h->model_stride; p.stage_bytes = h->stage_bytes;
   p.w0g_bytes = h->w0g_bytes; p.w2chunk_bytes = h->w2chunk_bytes; p.off_w2 = h->off_w2;
   p.off_w0g = h->off_w0g; p.bias = h->bias; p.norm = h->norm; p.pol = h->pol;
@@ -417,7 +457,7 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
   p.off_sw2 = h->off_sw2; p.off_sbias = h->off_sbias; p.off_snorm = h->off_snorm;
   p.off_spol = h->off_spol; p.off_bars = h->off_bars;
   int n_slots = 0;
-  int rc = get_schedule(h, p.n_steps, &p.segs, &n_slots, st);
+  int rc = get_schedule(h, p.n_steps, p.per_model ? p.n_tiles : 0, &p.segs, &n_slots, st);
   if (rc != METRPO_OK) return rc;
   p.n_slots = n_slots;
   METRPO_CUDA_OK(cudaMemsetAsync(h->xctr, 0, h->max_slots * 4, st));
@@ -452,6 +492,31 @@ extern "C" int metrpo_rollout_run(metrpo_rollout_t* h, int n_steps, const float*
   int rc = launch(h, p, static_cast<cudaStream_t>(stream_));
   if (rc == METRPO_OK) h->state_set = true;
   return rc;
+}
+
+extern "C" int metrpo_rollout_model_costs(metrpo_rollout_t* h, int n_steps, int n_rows,
+                                          const float* init_states, double gamma, float* row_costs,
+                                          float* model_costs, void* stream_) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "model_costs: null handle");
+  if (n_steps < 1) return set_error(METRPO_ERR_INVALID, "model_costs: n_steps must be >= 1");
+  if (n_rows < 1 || n_rows > h->cfg.n_envs)
+    return set_error(METRPO_ERR_INVALID, "model_costs: n_rows must be in [1, n_envs=%d]", h->cfg.n_envs);
+  if (!init_states || !model_costs) return set_error(METRPO_ERR_INVALID, "model_costs: init_states and model_costs are required");
+  if (!h->pol_set) return set_error(METRPO_ERR_STATE, "model_costs: policy was never set");
+  METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  KParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n_steps = n_steps; p.resume = 0; p.determ = 1; p.per_model = 1; p.B = n_rows;
+  p.gamma = static_cast<float>(gamma);
+  p.pm_cost = row_costs ? row_costs : h->pm_cost;
+  p.init_states = init_states; p.R = 1;
+  int rc = launch(h, p, st);
+  if (rc != METRPO_OK) return rc;
+  mean_rows_kernel<<<h->cfg.n_models, 256, 0, st>>>(p.pm_cost, model_costs, n_rows);
+  METRPO_CUDA_OK(cudaGetLastError());
+  h->last_launches = 2;
+  return METRPO_OK;
 }
 
 extern "C" int metrpo_rollout_step(metrpo_rollout_t* h, const float* actions, const int32_t* model_idx,

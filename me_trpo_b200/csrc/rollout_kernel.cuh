@@ -96,6 +96,11 @@ struct KParams {
   int NC, KC;
   int n_steps, n_slots, n_tiles;
   int resume;            // 1: state comes from row_state (B1 step / continued run)
+  int per_model;         // 1: per-model validation-cost rollout (model_based_rl.py:122-142): every
+                         //    model rolls its OWN prediction forward with the deterministic policy,
+                         //    no exchange / reset / timeout; only the discounted cost is emitted
+  float gamma;           // per_model: discount (policy_opt_params.gamma)
+  float* pm_cost;        // per_model: [K][B] discounted cost of (model, row)
   int row_offset;        // global index of local row 0 (keys the Philox streams)
   // packed weights (per model: W1 stages | W2 chunks | W0 group tiles)
   const uint8_t* wstream;
@@ -660,6 +665,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
       bool ep_valid = false;
       int row = 0;
       bool valid = false;
+      float pm_acc = 0.f, pm_gpow = 1.f, pm_dmask = 0.f;   // per_model: cost sum, gamma^t, Ant dones
       auto load_eps = [&](int tt) {
         if (p.eps != nullptr) {
 #pragma unroll
@@ -699,6 +705,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
 #pragma unroll
           for (int s = 0; s < SMAX; ++s) x[s] = (valid && s < S) ? p.init_states[row * S + s] : 0.f;
           ts = 0; nreset = 0;
+          pm_acc = 0.f; pm_gpow = 1.f; pm_dmask = 0.f;
         } else {
 #pragma unroll
           for (int s = 0; s < SMAX; ++s)
@@ -883,7 +890,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           }
           float xnext[SMAX];
           const int mode = p.sam_mode;
-          if (K == 1) {
+          if (K == 1 || p.per_model) {
 #pragma unroll
             for (int s = 0; s < SMAX; ++s) xnext[s] = cand[s];
           } else {
@@ -994,6 +1001,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
 #pragma unroll
           for (int i = 0; i < AMAX; ++i) u[i] = fminf(fmaxf(a_raw[i], -1.f), 1.f);
           const float reward = -env_cost(p.env_id, S, A, xnext, u);
+          if (p.per_model) {
+            // _policy_cost += gamma**t * cost_tf(x, u, x_next[, dones]); dones = max(dones,
+            // is_done_tf(x, x_next)) AFTER the cost (model_based_rl.py:133-139; Ant masks the cost
+            // of rows that already terminated, envs/com_ant_env.py:70-75)
+            const float c = __fmul_rn(-reward, 1.f - pm_dmask);
+            pm_acc = __fadd_rn(pm_acc, __fmul_rn(pm_gpow, c));
+            pm_gpow = __fmul_rn(pm_gpow, p.gamma);
+            if (env_is_done(p.env_id, S, xnext)) pm_dmask = 1.f;
+#pragma unroll
+            for (int s = 0; s < SMAX; ++s) x[s] = xnext[s];
+            continue;
+          }
           ts += 1;
           const bool dn = env_is_done(p.env_id, S, xnext) || (ts >= p.T_max);   // :603-604
           if (k == 0 && valid) {
@@ -1033,7 +1052,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
         }  // t
 
         // ---- segment end: publish the tile's state ----
-        if (k == 0) {
+        if (p.per_model) {
+          if (valid) p.pm_cost[static_cast<size_t>(k) * p.B + row] = pm_acc;
+        } else if (k == 0) {
           if (valid) {
 #pragma unroll
             for (int s = 0; s < SMAX; ++s)

@@ -167,6 +167,22 @@ class EnsembleRollout:
         self._keep = self._keep[-8:] + [(init, pool, ep, mi, sn)]
         return out
 
+    # -- R12: per-model validation cost (build_policy_graph, model_based_rl.py:122-142) --------
+    def model_costs(self, n_steps, init_states, gamma=1.0, return_rows=False):
+        """[K] discounted cost of the deterministic policy under each model rolled forward on its
+        own predictions from init_states[n_rows,S] (n_rows <= n_envs)."""
+        dev = self.device
+        init = _f32(init_states, dev)
+        n = int(init.shape[0])
+        assert init.dim() == 2 and init.shape[1] == self.S and 1 <= n <= self.B
+        rows = torch.empty(self.K, n, device=dev)
+        costs = torch.empty(self.K, device=dev)
+        _lib.check(self._lib.metrpo_rollout_model_costs(
+            self._h, int(n_steps), n, _lib.ptr(init), float(gamma), _lib.ptr(rows), _lib.ptr(costs),
+            _lib.stream_ptr()), "model_costs")
+        self._keep = self._keep[-8:] + [(init,)]
+        return (costs, rows) if return_rows else costs
+
     def synchronize(self):
         """Wait for the stream and raise if the last kernel aborted on an internal wait timeout."""
         _lib.check(self._lib.metrpo_rollout_status(self._h, _lib.stream_ptr()), "rollout kernel")

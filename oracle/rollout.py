@@ -324,3 +324,45 @@ def paths_from_flat(flat, log_std):
                                  log_std=np.broadcast_to(log_std, (L, len(log_std))).copy())))
             start[b] = t + 1
     return paths
+
+
+# ------------------------------------------------------------------------------------------------
+# build_policy_graph restatement (per-model validation cost; R12)
+# ------------------------------------------------------------------------------------------------
+def cost_tf(env, x, u, x_next, dones=None):
+    """envs/com_*_env.py cost_tf: batch MEAN of the per-row cost; Ant's takes the running `dones`
+    mask and zeroes the rows that already terminated (envs/com_ant_env.py:70-75)."""
+    c = _envs.cost_np_vec(env, x, u, x_next)
+    if dones is not None:
+        c = c * (1 - dones)
+    return np.mean(c, dtype=c.dtype)
+
+
+def model_costs(env, pol, models, norm, init_states, n_steps, gamma=1.0, out_tanh=False,
+                dtype=np.float32, mma="fp32", return_rows=False):
+    """model_based_rl.py:122-142: for each model i, x <- init; for t < T: u = clip(policy(x)) with
+    stochastic = 0 (:130), x' = dynamics_model_i([x,u]) (:132-134), cost += gamma**t *
+    cost_tf(x,u,x'[,dones]) (:136-141), dones = max(dones, is_done_tf(x,x')) after the cost (Ant
+    only, :137), x <- x'.  Returns [K] (and the per-row discounted sums [K,B])."""
+    name = _envs.env_name(env)
+    spec = _envs.ENV_SPECS[name]
+    S, drop = spec["S"], spec["drop"]
+    K, B = len(models), len(init_states)
+    costs = np.zeros(K, dtype)
+    rows = np.zeros((K, B), dtype)
+    for i, m in enumerate(models):
+        x = np.array(init_states, dtype)
+        dones = np.zeros(B, dtype) if name == "ant" else None
+        for t in range(n_steps):
+            u = np.clip(_models.policy_forward(pol, x, dtype, out_tanh), -1.0, 1.0).astype(dtype)
+            x_next = _models.dynamics_forward(m, norm, np.concatenate([x, u], 1), S, drop, dtype, mma)
+            g = dtype(gamma ** t)
+            c_rows = _envs.cost_np_vec(name, x, u, x_next).astype(dtype)
+            if dones is not None:
+                c_rows = c_rows * (1 - dones)
+            costs[i] += g * cost_tf(name, x, u, x_next, dones)
+            rows[i] += g * c_rows
+            if dones is not None:
+                dones = np.maximum(dones, _envs.is_done(name, x, x_next).astype(dtype))
+            x = x_next
+    return (costs, rows) if return_rows else costs
