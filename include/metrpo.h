@@ -271,6 +271,64 @@ int metrpo_trpo_grad(metrpo_trpo_t* h, long long N, const float* obs, const floa
                      int old_log_std_per_sample, const uint8_t* valid, const float* theta,
                      const float* vec, double reg_coeff, double* out_host, void* stream);
 
+/* =============================================================================================
+ * Ensemble dynamics fit: optimize_models (model_based_rl.py:881-1051) with the
+ * graph of build_dynamics_graph (:23-103) and get_dynamics_optimizer (:154-183).  All K models
+ * train on independent minibatches in one stream of kernels; weights, Adam moments and the
+ * per-model best snapshots live on the device in fp32.  x rows are [state, action] (S + A),
+ * y rows are next states (S) -- the data_collection layout (utils.py:44-131).
+ * ============================================================================================= */
+enum { METRPO_FIT_TF32 = 0,   /* GEMMs on TF32 tensor cores, fp32 accumulate (default) */
+       METRPO_FIT_FP32 = 1 }; /* GEMMs in true fp32 (the reference's tf.matmul arithmetic) */
+
+typedef struct {
+  int32_t state_dim;   /* S (<= 64) */
+  int32_t action_dim;  /* A */
+  int32_t drop_cols;   /* ignore_x_input / ignore_xy_input (training.py:146-154) */
+  int32_t hidden;      /* both hidden layers (multiple of 32) */
+  int32_t n_models;    /* K (<= 64) */
+  int32_t max_rows;    /* row capacity: >= dynamics_opt_params.batch_size; validation sets are
+                          processed in chunks of this many rows */
+  int32_t precision;   /* METRPO_FIT_* */
+  int32_t device;
+} metrpo_fit_cfg;
+
+typedef struct metrpo_fit metrpo_fit_t;
+
+int metrpo_fit_create(const metrpo_fit_cfg* cfg, metrpo_fit_t** out);
+int metrpo_fit_destroy(metrpo_fit_t* h);
+int metrpo_fit_num_params(const metrpo_fit_t* h);   /* trainable floats per model */
+int metrpo_fit_last_launches(const metrpo_fit_t* h);
+
+/* weights of model k in the TF layout W[in,out] (training.py:187-208); device fp32 */
+int metrpo_fit_set_weights(metrpo_fit_t* h, int k, const float* W0, const float* b0, const float* W1,
+                           const float* b1, const float* W2, const float* b2, void* stream);
+int metrpo_fit_get_weights(metrpo_fit_t* h, int k, float* W0, float* b0, float* W1, float* b1,
+                           float* W2, float* b2, void* stream);
+/* RunningMeanStd constants used inside dynamics_model (training.py:228,257) */
+int metrpo_fit_set_normalization(metrpo_fit_t* h, const float* in_mean, const float* in_std,
+                                 const float* diff_mean, const float* diff_std, void* stream);
+/* sess.run(dynamics_adam_init) (model_based_rl.py:906-918): zero moments, step count 0 */
+int metrpo_fit_reset_adam(metrpo_fit_t* h, void* stream);
+
+/* One training iteration (model_based_rl.py:957-970): row r of model k's minibatch is sample
+ * idx[r*K + k] of (x[n_data,S+A], y[n_data,S]) -- np.reshape(x_batch, (batch, -1)) +
+ * get_ith_tensor (utils.py:366-369); idx == NULL draws with replacement from Philox(seed, offset)
+ * (data_collection.sample, utils.py:129-131).  Loss of model k = mean_rows sum_s (pred - y)^2 on
+ * the de-normalised next state (:57-71); Adam(lr, 0.9, 0.999, 1e-8) in TF's formulation.
+ * losses [K] device floats (pre-update training losses) or NULL. */
+int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, int n_data, const int32_t* idx,
+                    int batch, uint64_t seed, uint64_t offset, double lr, float* losses, void* stream);
+
+/* Per-model loss on (x[n,S+A], y[n,S]) evaluated by ALL K models (np.tile, :934-935) ->
+ * losses [K] device floats.  snapshot 0: nothing; 1: models whose loss is below their recorded
+ * minimum are saved and the minimum updated (:998-1007); 2: save all and initialise the minima
+ * (:925-946).  improved [K] device bytes or NULL.  No host synchronisation. */
+int metrpo_fit_eval(metrpo_fit_t* h, const float* x, const float* y, int n, int snapshot, float* losses,
+                    uint8_t* improved, void* stream);
+/* recover_weights (:876-879,1034): every model back to its best snapshot */
+int metrpo_fit_restore_best(metrpo_fit_t* h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

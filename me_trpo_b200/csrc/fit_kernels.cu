@@ -1,0 +1,546 @@
+// Ensemble dynamics fit on the device (include/metrpo.h metrpo_fit_*), SURVEY.md 8(f) N3:
+//
+//   metrpo_fit_step   one optimizer step of ALL K models of the ensemble on K independent
+//                     minibatches (model_based_rl.py:957-970; utils.py:129-131,366-369):
+//                     gather + normalise -> MLP forward -> de-normalised MSE loss
+//                     (model_based_rl.py:57-71 with training.py:257) -> backward -> Adam
+//                     (tf.train.AdamOptimizer, model_based_rl.py:154-163)
+//   metrpo_fit_eval   per-model validation loss over a whole data set tiled K times (:934-935,
+//                     :973-981) + per-model best-weights snapshot (:998-1007), all on the device
+//   metrpo_fit_restore_best   recover_weights (:876-879, :1034)
+//
+// The three GEMM shapes per layer and direction (forward, dgrad, wgrad; 1000 x 1024 x 1024 for the
+// big layer) are plain dense GEMMs and go to cuBLAS (strided-batched over the K models, TF32
+// tensor cores with fp32 accumulate by default, or true fp32); everything between them is
+// hand-written and fused: gather+normalise+column-drop, bias+ReLU, the MSE backward (bias b2,
+// de-normalisation, residual, loss reduction, dO and db2 in one pass), ReLU-mask + bias-gradient
+// column sums, and one Adam kernel over the K x P flat parameter block.  All of these are HBM
+// bound; DESIGN.md lists their bytes per element.
+#include <cublas_v2.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace metrpo {
+
+constexpr uint32_t PHILOX_STREAM_FIT = 0x30000u;   // minibatch row indices
+
+struct FitDims {
+  int S, A, SA, drop, Din, H, K;
+  int oW0, ob0, oW1, ob1, oW2, ob2, P;   // float offsets inside one model's parameter block
+};
+
+// x_data[n][SA] (state, action), y_data[n][S] (next state).  Row r of model k's minibatch is sample
+// idx[r*K + k] (np.reshape(x_batch, (batch, -1)) + get_ith_tensor, model_based_rl.py:966-969,
+// utils.py:366-369); idx == NULL -> Philox; identity != 0 -> row0 + r for every model (validation:
+// np.tile(x, n_models), :934-935).
+__global__ void fit_gather_kernel(FitDims d, const float* __restrict__ x_data, const float* __restrict__ y_data,
+                                  int n_data, const int* __restrict__ idx, int identity, int row0,
+                                  unsigned long long seed, unsigned long long offset, int rows,
+                                  const float* __restrict__ norm, float* __restrict__ Z,
+                                  float* __restrict__ XS, float* __restrict__ Y, long long strideZ,
+                                  long long strideS) {
+  const int r = blockIdx.x * blockDim.y + threadIdx.y, k = blockIdx.y;
+  if (r >= rows) return;
+  int i;
+  if (identity) i = row0 + r;
+  else if (idx) i = idx[static_cast<size_t>(r) * d.K + k];
+  else i = philox_index(seed, static_cast<uint32_t>(offset), static_cast<uint32_t>(r * d.K + k), PHILOX_STREAM_FIT, n_data);
+  i = min(max(i, 0), n_data - 1);
+  const float* xr = x_data + static_cast<size_t>(i) * d.SA;
+  const float* yr = y_data + static_cast<size_t>(i) * d.S;
+  const float* in_mean = norm;
+  const float* in_std = norm + d.SA;
+  float* z = Z + k * strideZ + static_cast<size_t>(r) * d.Din;
+  float* xs = XS + k * strideS + static_cast<size_t>(r) * d.S;
+  float* y = Y + k * strideS + static_cast<size_t>(r) * d.S;
+  for (int c = threadIdx.x; c < d.SA; c += blockDim.x) {
+    const float v = xr[c];
+    if (c >= d.drop) z[c - d.drop] = __fdiv_rn(__fsub_rn(v, in_mean[c]), in_std[c]);   // training.py:228,146-154
+    if (c < d.S) { xs[c] = v; y[c] = yr[c]; }
+  }
+}
+
+// H = relu(H + b)  (training.py:207-208), float4 over [K][rows][Hd]
+__global__ void fit_bias_relu_kernel(float* __restrict__ Hbuf, const float* __restrict__ theta, int b_off,
+                                     long long P, int rows, int Hd, long long strideH) {
+  const int k = blockIdx.y;
+  const long long n4 = static_cast<long long>(rows) * Hd / 4;
+  float4* h4 = reinterpret_cast<float4*>(Hbuf + k * strideH);
+  const float4* b4 = reinterpret_cast<const float4*>(theta + k * P + b_off);
+  const int hq = Hd / 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = h4[i];
+    const float4 b = b4[i % hq];
+    v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f);
+    v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
+    h4[i] = v;
+  }
+}
+
+// Fused MSE forward/backward of the output layer.  One warp per (model, row):
+//   pred = (diff_mean + diff_std * (O + b2)) + x                       (training.py:257)
+//   loss_k += sum_s (pred - y)^2 * inv_rows                            (model_based_rl.py:57-71)
+//   dO = 2 * inv_rows * diff_std * (pred - y)   (in place, backward only);  db2 partials per block
+__global__ void fit_mse_kernel(FitDims d, float* __restrict__ O, const float* __restrict__ XS,
+                               const float* __restrict__ Y, const float* __restrict__ theta,
+                               const float* __restrict__ norm, int rows, double inv_rows, int backward,
+                               long long strideS, double* __restrict__ loss_acc, float* __restrict__ part2) {
+  const int k = blockIdx.y;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const float* b2 = theta + static_cast<size_t>(k) * d.P + d.ob2;
+  const float* dmean = norm + 2 * d.SA;
+  const float* dstd = norm + 2 * d.SA + d.S;
+  extern __shared__ float sh_db2[];   // [warps][S] per block
+  double lsum = 0.0;
+  float db_local[2] = {0.f, 0.f};   // lane owns columns lane, lane + 32 (S <= 64)
+  for (int r = blockIdx.x * wpb + wib; r < rows; r += gridDim.x * wpb) {
+    const size_t base = k * strideS + static_cast<size_t>(r) * d.S;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int s = lane + 32 * q;
+      if (s < d.S) {
+        const float o = __fadd_rn(O[base + s], b2[s]);
+        const float pred = __fadd_rn(__fadd_rn(dmean[s], __fmul_rn(dstd[s], o)), XS[base + s]);
+        const float diff = __fsub_rn(pred, Y[base + s]);
+        lsum += static_cast<double>(diff) * diff;
+        if (backward) {
+          const float g = static_cast<float>(2.0 * inv_rows) * dstd[s] * diff;
+          O[base + s] = g;
+          db_local[q] += g;
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if (lane == 0) atomicAdd(&loss_acc[k], lsum * inv_rows);
+  if (backward) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int s = lane + 32 * q;
+      if (s < d.S) sh_db2[wib * d.S + s] = db_local[q];
+    }
+    __syncthreads();
+    // per-block partial of db2, warps and blocks summed in a fixed order (bit-reproducible)
+    for (int s = threadIdx.x; s < d.S; s += blockDim.x) {
+      float acc = 0.f;
+      for (int w = 0; w < wpb; ++w) acc += sh_db2[w * d.S + s];
+      part2[(static_cast<size_t>(k) * gridDim.x + blockIdx.x) * d.S + s] = acc;
+    }
+  }
+}
+
+// dH *= (Hact > 0);  db[j] += sum_rows dH[., j].  Block = (32-column strip, 128-row slab, model):
+// 8 x 32 threads, one float4 per thread and row, column sums reduced through shared memory and
+// written as one partial row per slab (summed in a fixed order by fit_bias_grad_finish_kernel, so
+// the update is bit-reproducible).
+constexpr int COLSUM_ROWS = 128;
+__global__ void fit_relu_bwd_colsum_kernel(float* __restrict__ dH, const float* __restrict__ Hact, int rows,
+                                           int Hd, long long strideH, float* __restrict__ part_out) {
+  const int k = blockIdx.z, c4 = blockIdx.x * 8 + threadIdx.x;   // float4 column index
+  float4* g = reinterpret_cast<float4*>(dH + k * strideH);
+  const float4* a = reinterpret_cast<const float4*>(Hact + k * strideH);
+  const int hq = Hd / 4;
+  const int r_end = min(rows, (blockIdx.y + 1) * COLSUM_ROWS);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int r = blockIdx.y * COLSUM_ROWS + threadIdx.y; r < r_end; r += 32) {
+    const size_t o = static_cast<size_t>(r) * hq + c4;
+    const float4 av = a[o];
+    float4 v = g[o];
+    v.x = av.x > 0.f ? v.x : 0.f; v.y = av.y > 0.f ? v.y : 0.f;
+    v.z = av.z > 0.f ? v.z : 0.f; v.w = av.w > 0.f ? v.w : 0.f;
+    g[o] = v;
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  __shared__ float part[32][33];
+  part[threadIdx.y][threadIdx.x * 4 + 0] = acc.x;
+  part[threadIdx.y][threadIdx.x * 4 + 1] = acc.y;
+  part[threadIdx.y][threadIdx.x * 4 + 2] = acc.z;
+  part[threadIdx.y][threadIdx.x * 4 + 3] = acc.w;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int c = threadIdx.x; c < 32; c += 8) {
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += part[j][c];
+      part_out[(static_cast<size_t>(k) * gridDim.y + blockIdx.y) * Hd + blockIdx.x * 32 + c] = sum;
+    }
+  }
+}
+
+// db1, db0, db2 = fixed-order sums of the per-slab / per-block partials
+__global__ void fit_bias_grad_finish_kernel(FitDims d, const float* __restrict__ part1, const float* __restrict__ part0,
+                                            int nslab, const float* __restrict__ part2, int nblk2,
+                                            float* __restrict__ grad) {
+  const int k = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  float* g = grad + static_cast<size_t>(k) * d.P;
+  if (j < 2 * d.H) {
+    const float* p = (j < d.H ? part1 : part0) + static_cast<size_t>(k) * nslab * d.H + (j < d.H ? j : j - d.H);
+    float s = 0.f;
+    for (int b = 0; b < nslab; ++b) s += p[static_cast<size_t>(b) * d.H];
+    g[(j < d.H ? d.ob1 : d.ob0) + (j < d.H ? j : j - d.H)] = s;
+  } else if (j < 2 * d.H + d.S) {
+    const int c = j - 2 * d.H;
+    const float* p = part2 + static_cast<size_t>(k) * nblk2 * d.S + c;
+    float s = 0.f;
+    for (int b = 0; b < nblk2; ++b) s += p[static_cast<size_t>(b) * d.S];
+    g[d.ob2 + c] = s;
+  }
+}
+
+// tf.train.AdamOptimizer: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+// theta -= lr_t * m / (sqrt(v) + eps),  lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)  (host-computed)
+__global__ void fit_adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+                                float* __restrict__ v, long long n4, float lr_t, float beta1, float beta2,
+                                float eps) {
+  float4* t4 = reinterpret_cast<float4*>(theta);
+  const float4* g4 = reinterpret_cast<const float4*>(grad);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 t = t4[i], mm = m4[i], vv = v4[i];
+    const float4 g = g4[i];
+#define ADAM1(c)                                                     \
+    mm.c = beta1 * mm.c + (1.f - beta1) * g.c;                       \
+    vv.c = beta2 * vv.c + (1.f - beta2) * g.c * g.c;                 \
+    t.c = t.c - lr_t * mm.c / (sqrtf(vv.c) + eps);
+    ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+    t4[i] = t; m4[i] = mm; v4[i] = vv;
+  }
+}
+
+// per-model snapshot decision (model_based_rl.py:998-1007): mode 1: improved = min > new;
+// mode 2: unconditional (initial save, :925-930, :938-946)
+__global__ void fit_snapshot_flags_kernel(const double* __restrict__ loss_acc, float* __restrict__ min_losses,
+                                          uint8_t* __restrict__ flags, float* __restrict__ losses_out, int K,
+                                          int mode) {
+  const int k = threadIdx.x;
+  if (k >= K) return;
+  const float l = static_cast<float>(loss_acc[k]);
+  if (losses_out) losses_out[k] = l;
+  uint8_t f = 0;
+  if (mode == 2 || (mode == 1 && min_losses[k] > l)) { f = 1; min_losses[k] = l; }
+  flags[k] = f;
+}
+__global__ void fit_snapshot_copy_kernel(const float* __restrict__ theta, float* __restrict__ best,
+                                         const uint8_t* __restrict__ flags, long long P4) {
+  const int k = blockIdx.y;
+  if (!flags[k]) return;
+  const float4* s = reinterpret_cast<const float4*>(theta) + k * P4;
+  float4* t = reinterpret_cast<float4*>(best) + k * P4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < P4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    t[i] = s[i];
+}
+__global__ void fit_losses_out_kernel(const double* __restrict__ loss_acc, float* __restrict__ out, int K) {
+  if (threadIdx.x < K) out[threadIdx.x] = static_cast<float>(loss_acc[threadIdx.x]);
+}
+
+}  // namespace metrpo
+
+using namespace metrpo;
+
+struct metrpo_fit {
+  metrpo_fit_cfg cfg;
+  FitDims d;
+  long long P_pad;        // floats between consecutive models' parameter blocks (multiple of 4)
+  int R;                  // row capacity of the activation buffers
+  cublasHandle_t blas = nullptr;
+  cublasComputeType_t compute;
+  float *theta = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr, *best = nullptr;
+  float *Z = nullptr, *XS = nullptr, *Y = nullptr, *H0 = nullptr, *H1 = nullptr, *O = nullptr, *D1 = nullptr;
+  float* norm = nullptr;
+  float *part1 = nullptr, *part0 = nullptr, *part2 = nullptr;   // bias-gradient partials
+  double* loss_acc = nullptr;
+  float* min_losses = nullptr;
+  uint8_t* flags = nullptr;
+  long long adam_t = 0;
+  bool norm_set = false;
+  std::vector<char> w_set;
+  int last_launches = 0;
+};
+
+static void fit_free(metrpo_fit* h) {
+  if (!h) return;
+  if (h->blas) cublasDestroy(h->blas);
+  cudaFree(h->theta); cudaFree(h->grad); cudaFree(h->m); cudaFree(h->v); cudaFree(h->best);
+  cudaFree(h->Z); cudaFree(h->XS); cudaFree(h->Y); cudaFree(h->H0); cudaFree(h->H1); cudaFree(h->O);
+  cudaFree(h->D1); cudaFree(h->norm); cudaFree(h->part1); cudaFree(h->part0); cudaFree(h->part2); cudaFree(h->loss_acc); cudaFree(h->min_losses); cudaFree(h->flags);
+  delete h;
+}
+
+#define METRPO_BLAS_OK(expr)                                                                     \
+  do {                                                                                           \
+    cublasStatus_t _s = (expr);                                                                  \
+    if (_s != CUBLAS_STATUS_SUCCESS)                                                             \
+      return set_error(METRPO_ERR_CUDA, "%s:%d: %s -> cublas status %d", __FILE__, __LINE__, #expr, (int)_s); \
+  } while (0)
+
+extern "C" int metrpo_fit_create(const metrpo_fit_cfg* cfg, metrpo_fit_t** out) {
+  if (!cfg || !out) return set_error(METRPO_ERR_INVALID, "fit_create: null argument");
+  *out = nullptr;
+  const metrpo_fit_cfg& c = *cfg;
+  if (c.state_dim < 1 || c.action_dim < 1 || c.n_models < 1 || c.max_rows < 1)
+    return set_error(METRPO_ERR_INVALID, "fit_create: S, A, K, max_rows must be >= 1");
+  if (c.state_dim > 64 || c.n_models > 64) return set_error(METRPO_ERR_UNSUPPORTED, "fit_create: S <= 64 and K <= 64 in this build");
+  if (c.drop_cols < 0 || c.drop_cols > 2 || c.drop_cols >= c.state_dim)
+    return set_error(METRPO_ERR_INVALID, "fit_create: drop_cols must be 0, 1 or 2");
+  if (c.hidden < 32 || c.hidden % 32)
+    return set_error(METRPO_ERR_UNSUPPORTED, "fit_create: hidden width must be a multiple of 32 (got %d)", c.hidden);
+  if (c.precision != METRPO_FIT_TF32 && c.precision != METRPO_FIT_FP32)
+    return set_error(METRPO_ERR_INVALID, "fit_create: unknown precision %d", c.precision);
+  METRPO_CUDA_OK(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  METRPO_CUDA_OK(cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major != 10)
+    return set_error(METRPO_ERR_UNSUPPORTED, "fit_create: device %d is sm_%d%d; this library is sm_100a only (no fallback)", c.device, prop.major, prop.minor);
+
+  metrpo_fit* h = new metrpo_fit();
+  h->cfg = c;
+  FitDims& d = h->d;
+  d.S = c.state_dim; d.A = c.action_dim; d.SA = d.S + d.A; d.drop = c.drop_cols; d.Din = d.SA - d.drop;
+  d.H = c.hidden; d.K = c.n_models;
+  // every sub-block starts on a float4 boundary (H % 32 == 0; W0 and W2 are padded up)
+  auto up4 = [](int v) { return (v + 3) / 4 * 4; };
+  d.oW0 = 0; d.ob0 = up4(d.Din * d.H); d.oW1 = d.ob0 + d.H; d.ob1 = d.oW1 + d.H * d.H;
+  d.oW2 = d.ob1 + d.H; d.ob2 = d.oW2 + up4(d.H * d.S); d.P = d.ob2 + up4(d.S);
+  h->P_pad = d.P;
+  h->R = c.max_rows;
+  h->compute = c.precision == METRPO_FIT_FP32 ? CUBLAS_COMPUTE_32F : CUBLAS_COMPUTE_32F_FAST_TF32;
+  h->w_set.assign(d.K, 0);
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
+  };
+  const size_t PK = static_cast<size_t>(d.P) * d.K * 4, RK = static_cast<size_t>(h->R) * d.K * 4;
+  alloc((void**)&h->theta, PK); alloc((void**)&h->grad, PK); alloc((void**)&h->m, PK);
+  alloc((void**)&h->v, PK); alloc((void**)&h->best, PK);
+  alloc((void**)&h->Z, RK * d.Din); alloc((void**)&h->XS, RK * d.S); alloc((void**)&h->Y, RK * d.S);
+  alloc((void**)&h->H0, RK * d.H); alloc((void**)&h->H1, RK * d.H); alloc((void**)&h->D1, RK * d.H);
+  alloc((void**)&h->O, RK * d.S);
+  alloc((void**)&h->norm, (2 * d.SA + 2 * d.S) * 4);
+  const size_t nslab_max = (h->R + COLSUM_ROWS - 1) / COLSUM_ROWS;
+  alloc((void**)&h->part1, nslab_max * d.K * d.H * 4); alloc((void**)&h->part0, nslab_max * d.K * d.H * 4);
+  alloc((void**)&h->part2, static_cast<size_t>(148) * d.K * d.S * 4);
+  alloc((void**)&h->loss_acc, d.K * 8); alloc((void**)&h->min_losses, d.K * 4); alloc((void**)&h->flags, d.K);
+  if (e != cudaSuccess) {
+    fit_free(h);
+    return set_error(e == cudaErrorMemoryAllocation ? METRPO_ERR_NOMEM : METRPO_ERR_CUDA, "fit_create: %s", cudaGetErrorString(e));
+  }
+  if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) {
+    fit_free(h);
+    return set_error(METRPO_ERR_CUDA, "fit_create: cublasCreate failed");
+  }
+  *out = h;
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_fit_destroy(metrpo_fit_t* h) {
+  if (!h) return METRPO_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  fit_free(h);
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_fit_num_params(const metrpo_fit_t* h) {
+  if (!h) return 0;
+  const FitDims& d = h->d;
+  return d.Din * d.H + d.H + d.H * d.H + d.H + d.H * d.S + d.S;
+}
+extern "C" int metrpo_fit_last_launches(const metrpo_fit_t* h) { return h ? h->last_launches : 0; }
+
+static int fit_copy_weights(metrpo_fit* h, int k, float* const* user, bool to_lib, float* block, cudaStream_t st) {
+  const FitDims& d = h->d;
+  const int off[6] = {d.oW0, d.ob0, d.oW1, d.ob1, d.oW2, d.ob2};
+  const int len[6] = {d.Din * d.H, d.H, d.H * d.H, d.H, d.H * d.S, d.S};
+  float* base = block + static_cast<size_t>(k) * d.P;
+  for (int i = 0; i < 6; ++i) {
+    if (to_lib) METRPO_CUDA_OK(cudaMemcpyAsync(base + off[i], user[i], len[i] * 4, cudaMemcpyDeviceToDevice, st));
+    else METRPO_CUDA_OK(cudaMemcpyAsync(user[i], base + off[i], len[i] * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_fit_set_weights(metrpo_fit_t* h, int k, const float* W0, const float* b0, const float* W1,
+                                      const float* b1, const float* W2, const float* b2, void* stream) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "fit_set_weights: null handle");
+  if (k < 0 || k >= h->d.K) return set_error(METRPO_ERR_INVALID, "fit_set_weights: model index %d out of range", k);
+  if (!W0 || !b0 || !W1 || !b1 || !W2 || !b2) return set_error(METRPO_ERR_INVALID, "fit_set_weights: null weight pointer");
+  float* user[6] = {const_cast<float*>(W0), const_cast<float*>(b0), const_cast<float*>(W1),
+                    const_cast<float*>(b1), const_cast<float*>(W2), const_cast<float*>(b2)};
+  int rc = fit_copy_weights(h, k, user, true, h->theta, static_cast<cudaStream_t>(stream));
+  if (rc == METRPO_OK) h->w_set[k] = 1;
+  return rc;
+}
+
+extern "C" int metrpo_fit_get_weights(metrpo_fit_t* h, int k, float* W0, float* b0, float* W1, float* b1,
+                                      float* W2, float* b2, void* stream) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "fit_get_weights: null handle");
+  if (k < 0 || k >= h->d.K) return set_error(METRPO_ERR_INVALID, "fit_get_weights: model index %d out of range", k);
+  if (!W0 || !b0 || !W1 || !b1 || !W2 || !b2) return set_error(METRPO_ERR_INVALID, "fit_get_weights: null weight pointer");
+  float* user[6] = {W0, b0, W1, b1, W2, b2};
+  return fit_copy_weights(h, k, user, false, h->theta, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int metrpo_fit_set_normalization(metrpo_fit_t* h, const float* in_mean, const float* in_std,
+                                            const float* diff_mean, const float* diff_std, void* stream) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "fit_set_normalization: null handle");
+  if (!in_mean || !in_std || !diff_mean || !diff_std) return set_error(METRPO_ERR_INVALID, "fit_set_normalization: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int SA = h->d.SA, S = h->d.S;
+  METRPO_CUDA_OK(cudaMemcpyAsync(h->norm, in_mean, SA * 4, cudaMemcpyDeviceToDevice, st));
+  METRPO_CUDA_OK(cudaMemcpyAsync(h->norm + SA, in_std, SA * 4, cudaMemcpyDeviceToDevice, st));
+  METRPO_CUDA_OK(cudaMemcpyAsync(h->norm + 2 * SA, diff_mean, S * 4, cudaMemcpyDeviceToDevice, st));
+  METRPO_CUDA_OK(cudaMemcpyAsync(h->norm + 2 * SA + S, diff_std, S * 4, cudaMemcpyDeviceToDevice, st));
+  h->norm_set = true;
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_fit_reset_adam(metrpo_fit_t* h, void* stream) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "fit_reset_adam: null handle");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t PK = static_cast<size_t>(h->d.P) * h->d.K * 4;
+  METRPO_CUDA_OK(cudaMemsetAsync(h->m, 0, PK, st));
+  METRPO_CUDA_OK(cudaMemsetAsync(h->v, 0, PK, st));
+  h->adam_t = 0;
+  return METRPO_OK;
+}
+
+// row-major C[M,N] = op(A) op(B), batched over the K models (column-major cuBLAS sees the
+// transposes: C^T = op(B)^T op(A)^T)
+static cublasStatus_t gemm_rm(metrpo_fit* h, bool tA, bool tB, int M, int N, int Kd, const float* A, int lda,
+                              long long sA, const float* B, int ldb, long long sB, float* C, int ldc,
+                              long long sC) {
+  const float one = 1.f, zero = 0.f;
+  return cublasGemmStridedBatchedEx(h->blas, tB ? CUBLAS_OP_T : CUBLAS_OP_N, tA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M,
+                                    Kd, &one, B, CUDA_R_32F, ldb, sB, A, CUDA_R_32F, lda, sA, &zero, C,
+                                    CUDA_R_32F, ldc, sC, h->d.K, h->compute, CUBLAS_GEMM_DEFAULT);
+}
+
+static int fit_check_ready(metrpo_fit* h, const char* who) {
+  for (int k = 0; k < h->d.K; ++k)
+    if (!h->w_set[k]) return set_error(METRPO_ERR_STATE, "%s: weights of model %d were never set", who, k);
+  if (!h->norm_set) return set_error(METRPO_ERR_STATE, "%s: normalization constants were never set", who);
+  return METRPO_OK;
+}
+
+// gather + forward of `rows` rows per model; leaves O = H1 W2 (bias b2 is added by fit_mse_kernel)
+static int fit_forward(metrpo_fit* h, const float* x, const float* y, int n_data, const int* idx, int identity,
+                       int row0, unsigned long long seed, unsigned long long offset, int rows, cudaStream_t st,
+                       int& launches) {
+  const FitDims& d = h->d;
+  const long long R = h->R, sZ = R * d.Din, sS = R * d.S, sH = R * d.H, P = d.P;
+  {
+    dim3 blk(32, 8), grd((rows + 7) / 8, d.K);
+    fit_gather_kernel<<<grd, blk, 0, st>>>(d, x, y, n_data, idx, identity, row0, seed, offset, rows, h->norm,
+                                          h->Z, h->XS, h->Y, sZ, sS);
+  }
+  METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.H, d.Din, h->Z, d.Din, sZ, h->theta + d.oW0, d.H, P, h->H0, d.H, sH));
+  const int eb = static_cast<int>(std::min<long long>((static_cast<long long>(rows) * d.H / 4 + 255) / 256, 1184));
+  fit_bias_relu_kernel<<<dim3(eb, d.K), 256, 0, st>>>(h->H0, h->theta, d.ob0, P, rows, d.H, sH);
+  METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.H, d.H, h->H0, d.H, sH, h->theta + d.oW1, d.H, P, h->H1, d.H, sH));
+  fit_bias_relu_kernel<<<dim3(eb, d.K), 256, 0, st>>>(h->H1, h->theta, d.ob1, P, rows, d.H, sH);
+  METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.S, d.H, h->H1, d.H, sH, h->theta + d.oW2, d.S, P, h->O, d.S, sS));
+  METRPO_CUDA_OK(cudaGetLastError());
+  launches += 6;
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, int n_data, const int32_t* idx,
+                               int batch, uint64_t seed, uint64_t offset, double lr, float* losses,
+                               void* stream) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "fit_step: null handle");
+  if (!x || !y || n_data < 1) return set_error(METRPO_ERR_INVALID, "fit_step: x, y and n_data >= 1 are required");
+  if (batch < 1 || batch > h->R) return set_error(METRPO_ERR_INVALID, "fit_step: batch must be in [1, max_rows=%d]", h->R);
+  int rc = fit_check_ready(h, "fit_step");
+  if (rc != METRPO_OK) return rc;
+  METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  METRPO_BLAS_OK(cublasSetStream(h->blas, st));
+  const FitDims& d = h->d;
+  const long long R = h->R, sZ = R * d.Din, sS = R * d.S, sH = R * d.H, P = d.P;
+  int launches = 0;
+  METRPO_CUDA_OK(cudaMemsetAsync(h->loss_acc, 0, d.K * 8, st));
+  rc = fit_forward(h, x, y, n_data, idx, 0, 0, seed, offset, batch, st, launches);
+  if (rc != METRPO_OK) return rc;
+  const int mb = std::min((batch + 7) / 8, 148);
+  fit_mse_kernel<<<dim3(mb, d.K), 256, 8 * d.S * 4, st>>>(d, h->O, h->XS, h->Y, h->theta, h->norm, batch, 1.0 / batch, 1,
+                                                     sS, h->loss_acc, h->part2);
+  // dW2[H,S] = H1^T dO;  dH1 = dO W2^T (masked by H1 > 0, db1 = column sums)
+  METRPO_BLAS_OK(gemm_rm(h, true, false, d.H, d.S, batch, h->H1, d.H, sH, h->O, d.S, sS, h->grad + d.oW2, d.S, P));
+  METRPO_BLAS_OK(gemm_rm(h, false, true, batch, d.H, d.S, h->O, d.S, sS, h->theta + d.oW2, d.S, P, h->D1, d.H, sH));
+  fit_relu_bwd_colsum_kernel<<<dim3(d.H / 32, (batch + COLSUM_ROWS - 1) / COLSUM_ROWS, d.K), dim3(8, 32), 0, st>>>(h->D1, h->H1, batch, d.H, sH, h->part1);
+  // dW1 = H0^T dH1;  dH0 = dH1 W1^T -> H1's buffer (H1 is dead now), masked by H0 > 0, db0
+  METRPO_BLAS_OK(gemm_rm(h, true, false, d.H, d.H, batch, h->H0, d.H, sH, h->D1, d.H, sH, h->grad + d.oW1, d.H, P));
+  METRPO_BLAS_OK(gemm_rm(h, false, true, batch, d.H, d.H, h->D1, d.H, sH, h->theta + d.oW1, d.H, P, h->H1, d.H, sH));
+  fit_relu_bwd_colsum_kernel<<<dim3(d.H / 32, (batch + COLSUM_ROWS - 1) / COLSUM_ROWS, d.K), dim3(8, 32), 0, st>>>(h->H1, h->H0, batch, d.H, sH, h->part0);
+  // dW0[Din,H] = Z^T dH0
+  METRPO_BLAS_OK(gemm_rm(h, true, false, d.Din, d.H, batch, h->Z, d.Din, sZ, h->H1, d.H, sH, h->grad + d.oW0, d.H, P));
+  fit_bias_grad_finish_kernel<<<dim3((2 * d.H + d.S + 255) / 256, d.K), 256, 0, st>>>(
+      d, h->part1, h->part0, (batch + COLSUM_ROWS - 1) / COLSUM_ROWS, h->part2, mb, h->grad);
+  // Adam (tf.train.AdamOptimizer defaults beta1 0.9, beta2 0.999, epsilon 1e-8)
+  h->adam_t += 1;
+  const double b1 = 0.9, b2 = 0.999;
+  const double lr_t = lr * std::sqrt(1.0 - std::pow(b2, (double)h->adam_t)) / (1.0 - std::pow(b1, (double)h->adam_t));
+  const long long n4 = P * d.K / 4;
+  fit_adam_kernel<<<static_cast<int>(std::min<long long>((n4 + 255) / 256, 148 * 8)), 256, 0, st>>>(
+      h->theta, h->grad, h->m, h->v, n4, static_cast<float>(lr_t), 0.9f, 0.999f, 1e-8f);
+  launches += 10;
+  if (losses) { fit_losses_out_kernel<<<1, 64, 0, st>>>(h->loss_acc, losses, d.K); ++launches; }
+  METRPO_CUDA_OK(cudaGetLastError());
+  h->last_launches = launches;
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_fit_eval(metrpo_fit_t* h, const float* x, const float* y, int n, int snapshot, float* losses,
+                               uint8_t* improved, void* stream) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "fit_eval: null handle");
+  if (!x || !y || n < 1) return set_error(METRPO_ERR_INVALID, "fit_eval: x, y and n >= 1 are required");
+  if (snapshot < 0 || snapshot > 2) return set_error(METRPO_ERR_INVALID, "fit_eval: snapshot must be 0, 1 or 2");
+  if (h->d.K > 64) return set_error(METRPO_ERR_UNSUPPORTED, "fit_eval: K <= 64");
+  int rc = fit_check_ready(h, "fit_eval");
+  if (rc != METRPO_OK) return rc;
+  METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  METRPO_BLAS_OK(cublasSetStream(h->blas, st));
+  const FitDims& d = h->d;
+  const long long sS = static_cast<long long>(h->R) * d.S;
+  int launches = 0;
+  METRPO_CUDA_OK(cudaMemsetAsync(h->loss_acc, 0, d.K * 8, st));
+  for (int row0 = 0; row0 < n; row0 += h->R) {
+    const int rows = std::min(h->R, n - row0);
+    rc = fit_forward(h, x, y, n, nullptr, 1, row0, 0, 0, rows, st, launches);
+    if (rc != METRPO_OK) return rc;
+    const int mb = std::min((rows + 7) / 8, 148);
+    fit_mse_kernel<<<dim3(mb, d.K), 256, 8 * d.S * 4, st>>>(d, h->O, h->XS, h->Y, h->theta, h->norm, rows, 1.0 / n, 0, sS,
+                                                       h->loss_acc, h->part2);
+    ++launches;
+  }
+  fit_snapshot_flags_kernel<<<1, 64, 0, st>>>(h->loss_acc, h->min_losses, h->flags, losses, d.K, snapshot);
+  ++launches;
+  if (snapshot) {
+    fit_snapshot_copy_kernel<<<dim3(64, d.K), 256, 0, st>>>(h->theta, h->best, h->flags, d.P / 4);
+    ++launches;
+  }
+  if (improved) METRPO_CUDA_OK(cudaMemcpyAsync(improved, h->flags, d.K, cudaMemcpyDeviceToDevice, st));
+  METRPO_CUDA_OK(cudaGetLastError());
+  h->last_launches = launches;
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_fit_restore_best(metrpo_fit_t* h, void* stream) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "fit_restore_best: null handle");
+  METRPO_CUDA_OK(cudaMemcpyAsync(h->theta, h->best, static_cast<size_t>(h->d.P) * h->d.K * 4,
+                                 cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return METRPO_OK;
+}

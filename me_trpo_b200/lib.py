@@ -45,6 +45,14 @@ class TrpoCfg(ctypes.Structure):
     ]
 
 
+class FitCfg(ctypes.Structure):
+    _fields_ = [
+        ("state_dim", ctypes.c_int32), ("action_dim", ctypes.c_int32), ("drop_cols", ctypes.c_int32),
+        ("hidden", ctypes.c_int32), ("n_models", ctypes.c_int32), ("max_rows", ctypes.c_int32),
+        ("precision", ctypes.c_int32), ("device", ctypes.c_int32),
+    ]
+
+
 _vp, _i, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
 _ll, _d = ctypes.c_longlong, ctypes.c_double
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
@@ -78,6 +86,17 @@ _PROTOS = {
     "metrpo_trpo_update": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _d, _i, _d, _d, _i, _vp, _vp]),
     "metrpo_trpo_loss_kl": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "metrpo_trpo_grad": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _d, _vp, _vp]),
+    "metrpo_fit_create": (_i, [ctypes.POINTER(FitCfg), ctypes.POINTER(_vp)]),
+    "metrpo_fit_destroy": (_i, [_vp]),
+    "metrpo_fit_num_params": (_i, [_vp]),
+    "metrpo_fit_last_launches": (_i, [_vp]),
+    "metrpo_fit_set_weights": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "metrpo_fit_get_weights": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "metrpo_fit_set_normalization": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "metrpo_fit_reset_adam": (_i, [_vp, _vp]),
+    "metrpo_fit_step": (_i, [_vp, _vp, _vp, _i, _vp, _i, _u64, _u64, _d, _vp, _vp]),
+    "metrpo_fit_eval": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "metrpo_fit_restore_best": (_i, [_vp, _vp]),
 }
 
 _lib = None
