@@ -13,13 +13,13 @@ namespace metrpo {
 // ---------------------------------------------------------------------------------------------
 // packing kernels (one thread per destination element)
 // ---------------------------------------------------------------------------------------------
-// stage (nc,kc) = W1 tile: n in [256nc,+256) x k in [64kc,+64), SW128 K-major
+// stage (nc,kc) = W1 tile: n in [N1*nc,+N1) x k in [64kc,+64), SW128 K-major
 __global__ void pack_w1_kernel(const float* __restrict__ W1, uint8_t* __restrict__ dst, int H,
-                               int KC, uint32_t stage_bytes) {
+                               int KC, int N1, uint32_t stage_bytes) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<size_t>(H) * H) return;
   const int kglob = static_cast<int>(i / H), n = static_cast<int>(i % H);   // W1[k][n]
-  const int nc = n / 256, nl = n % 256, kc = kglob / 64, kl = kglob % 64;
+  const int nc = n / N1, nl = n % N1, kc = kglob / 64, kl = kglob % 64;
   uint8_t* st = dst + static_cast<size_t>(nc * KC + kc) * stage_bytes;
   *reinterpret_cast<__nv_bfloat16*>(st + sw128_off(nl, kl)) = __float2bfloat16_rn(W1[i]);
 }
@@ -39,13 +39,13 @@ __global__ void pack_w0_kernel(const float* __restrict__ W0, const float* __rest
   *reinterpret_cast<__nv_bfloat16*>(dst + off_w0g + static_cast<size_t>(j) * w0g_bytes +
                                     noswz_off(nl, kk, 128)) = __float2bfloat16_rn(val);
 }
-// W2 chunk nc: 4 sub-tiles [S_pad rows (s)][64 k] SW128, zero padded s >= S
+// W2 chunk nc: N1/64 sub-tiles [S_pad rows (s)][64 k] SW128, zero padded s >= S
 __global__ void pack_w2_kernel(const float* __restrict__ W2, uint8_t* __restrict__ dst, int H, int S,
-                               int S_pad, uint32_t off_w2, uint32_t w2chunk_bytes) {
+                               int S_pad, int N1, uint32_t off_w2, uint32_t w2chunk_bytes) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * S_pad) return;
   const int h = i / S_pad, s = i % S_pad;
-  const int nc = h / 256, sub = (h % 256) / 64, kl = h % 64;
+  const int nc = h / N1, sub = (h % N1) / 64, kl = h % 64;
   const float v = s < S ? W2[h * S + s] : 0.f;
   uint8_t* base = dst + off_w2 + static_cast<size_t>(nc) * w2chunk_bytes + sub * (S_pad * 128);
   *reinterpret_cast<__nv_bfloat16*>(base + sw128_off(s, kl)) = __float2bfloat16_rn(v);
@@ -53,7 +53,7 @@ __global__ void pack_w2_kernel(const float* __restrict__ W2, uint8_t* __restrict
 __global__ void pack_bias_kernel(const float* __restrict__ b0, const float* __restrict__ b1,
                                  const float* __restrict__ b2, float* __restrict__ dst, int H, int S) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * H + 32) return;
+  if (i >= 2 * H + BIAS_PAD) return;
   dst[i] = i < H ? b0[i] : (i < 2 * H ? b1[i - H] : (i - 2 * H < S ? b2[i - 2 * H] : 0.f));
 }
 __global__ void pack_policy_layer_kernel(const float* __restrict__ W, const float* __restrict__ b,
@@ -103,7 +103,11 @@ using namespace metrpo;
 // ---------------------------------------------------------------------------------------------
 struct metrpo_rollout {
   metrpo_rollout_cfg cfg;
-  int Din, K0, S_pad, NC, KC, n_tiles, max_slots, num_sms;
+  int Din, K0, S_pad, NC, KC, N1, n_tiles, max_slots, num_sms;
+  bool big;                       // <SMAX, AMAX> = <64, 24> instantiation (else <32, 8>)
+  int smax, amax;
+  uint32_t tm_acc0, tm_acc2, tm_h0, tm_z;
+  int pol_in_smem;
   uint32_t stage_bytes, w0g_bytes, w2chunk_bytes, off_w2, off_w0g;
   size_t model_stride;
   // device buffers
@@ -160,10 +164,15 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     return set_error(METRPO_ERR_INVALID, "create: unknown sam_mode %d", c.sam_mode);
   if (c.precision != METRPO_PREC_BF16)
     return set_error(METRPO_ERR_UNSUPPORTED, "create: only METRPO_PREC_BF16 is implemented");
-  if (c.hidden < 256 || c.hidden % 256)
-    return set_error(METRPO_ERR_UNSUPPORTED, "create: dynamics hidden width must be a multiple of 256 (got %d)", c.hidden);
-  if (c.state_dim > SMAX || c.action_dim > AMAX)
-    return set_error(METRPO_ERR_UNSUPPORTED, "create: this build covers S <= %d, A <= %d (got %d, %d)", SMAX, AMAX, c.state_dim, c.action_dim);
+  {
+    bool big = c.state_dim > 32 || c.action_dim > 8;
+    for (int l = 1; l < c.n_policy_layers && l < METRPO_MAX_POLICY_LAYERS; ++l) big = big || c.policy_dims[l] > HPB;
+    const int mult = big ? 128 : 256;
+    if (c.hidden < mult || c.hidden % mult)
+      return set_error(METRPO_ERR_UNSUPPORTED, "create: dynamics hidden width must be a multiple of %d (got %d)", mult, c.hidden);
+  }
+  if (c.state_dim > 64 || c.action_dim > 24)
+    return set_error(METRPO_ERR_UNSUPPORTED, "create: this build covers S <= 64, A <= 24 (got %d, %d)", c.state_dim, c.action_dim);
   if (c.n_policy_layers < 1 || c.n_policy_layers > METRPO_MAX_POLICY_LAYERS)
     return set_error(METRPO_ERR_INVALID, "create: n_policy_layers in [1,%d]", METRPO_MAX_POLICY_LAYERS);
   if (c.policy_dims[0] != c.state_dim || c.policy_dims[c.n_policy_layers] != c.action_dim)
@@ -190,13 +199,24 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   h->Din = c.state_dim + c.action_dim - c.drop_cols;
   h->K0 = static_cast<int>(align_up(h->Din + 2, 16));   // +2: ones columns carrying b0 (hi, lo)
   h->S_pad = static_cast<int>(align_up(c.state_dim, 16));
-  h->NC = c.hidden / 256;
+  h->big = c.state_dim > 32 || c.action_dim > 8;
+  for (int l = 1; l < c.n_policy_layers; ++l) h->big = h->big || c.policy_dims[l] > HPB;
+  h->smax = h->big ? 64 : 32;
+  h->amax = h->big ? 24 : 8;
+  // TMEM budget (512 columns): acc1 N1 | acc0 128 | acc2 S_pad | H0 64 | Z K0/2.  The wide layer-1
+  // pass (N1 = 256) is used whenever it fits; otherwise passes of 128 columns.
+  h->N1 = h->big ? 128 : 256;   // the two compiled instantiations
+  h->tm_acc0 = h->N1;
+  h->tm_acc2 = h->tm_acc0 + 128;
+  h->tm_h0 = h->tm_acc2 + std::max(h->S_pad, 32);
+  h->tm_z = h->tm_h0 + 64;
+  h->NC = c.hidden / h->N1;
   h->KC = c.hidden / 64;
   h->n_tiles = (c.n_envs + TILE_M - 1) / TILE_M;
   h->max_slots = std::min(h->n_tiles, h->num_sms / c.n_models);
   h->w0g_bytes = 128 * h->K0 * 2;
-  h->stage_bytes = W1_TILE_BYTES;
-  h->w2chunk_bytes = h->S_pad * 256 * 2;
+  h->stage_bytes = h->N1 * 64 * 2;
+  h->w2chunk_bytes = h->S_pad * h->N1 * 2;
   h->off_w2 = h->NC * h->KC * h->stage_bytes;
   h->off_w0g = h->off_w2 + h->NC * h->w2chunk_bytes;
   h->model_stride = align_up(h->off_w0g + (c.hidden / 128) * h->w0g_bytes, 1024);
@@ -208,22 +228,45 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     PolicyLayer& L = h->pl[l];
     L.nin = c.policy_dims[l];
     L.nout = c.policy_dims[l + 1];
-    L.npad = (l == c.n_policy_layers - 1) ? AMAX : HPMAX;
+    L.npad = (l == c.n_policy_layers - 1) ? h->amax : static_cast<int>(align_up(L.nout, HPB));
     L.w_off = off; off += L.nin * L.npad;
     L.b_off = off; off += L.npad;
   }
-  h->pol_logstd_off = off; off += AMAX;
+  h->pol_logstd_off = off; off += h->amax;
   h->pol_floats = off;
+  // activation rows of the policy in the scratch area: region A holds the layer-0 input (x) and
+  // doubles as the Z staging area [S+A rows]; a hidden layer of <= 32 outputs writes in place,
+  // a wider one writes to the other region
+  int region_rows[2] = {c.state_dim + c.action_dim, 0};
+  {
+    int cur = 0;
+    for (int l = 0; l < c.n_policy_layers; ++l) {
+      PolicyLayer& L = h->pl[l];
+      L.in_off = cur;   // region index for now
+      region_rows[cur] = std::max(region_rows[cur], L.nin);
+      if (l < c.n_policy_layers - 1) {
+        if (L.nout > HPB) cur ^= 1;
+        region_rows[cur] = std::max(region_rows[cur], L.nout);
+      }
+      L.out_off = cur;
+    }
+    for (int l = 0; l < c.n_policy_layers; ++l) {
+      PolicyLayer& L = h->pl[l];
+      L.in_off = L.in_off ? region_rows[0] * TILE_M : 0;
+      L.out_off = L.out_off ? region_rows[0] * TILE_M : 0;
+    }
+  }
+  h->pol_in_smem = !h->big || h->pol_floats * 4 <= 16 * 1024;
 
   // shared-memory carve-up (A operands live in TMEM; smem holds the weight ring + constants)
   uint32_t o = 0;
   h->off_stage = o; o += NSTAGE * h->stage_bytes;
   h->off_sw0g = o; o += 2 * h->w0g_bytes;
   o = align_up(o, 1024); h->off_sw2 = o; o += h->w2chunk_bytes;
-  h->off_scr = o; o += std::max(c.state_dim + c.action_dim, HPMAX) * TILE_M * 4;
-  h->off_sbias = o; o += (2 * c.hidden + 32) * 4;
+  h->off_scr = o; o += (region_rows[0] + region_rows[1]) * TILE_M * 4;
+  h->off_sbias = o; o += (2 * c.hidden + BIAS_PAD) * 4;
   h->off_snorm = o; o += align_up((2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4, 16);
-  h->off_spol = o; o += align_up(h->pol_floats * 4, 16);
+  h->off_spol = o; o += h->pol_in_smem ? align_up(h->pol_floats * 4, 16) : 0;
   h->off_bars = o; o += NUM_BARS * 8;
   h->smem_bytes = o + 1024;
   if (h->smem_bytes > static_cast<uint32_t>(prop.sharedMemPerBlockOptin)) {
@@ -231,9 +274,9 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     delete h;
     return set_error(METRPO_ERR_UNSUPPORTED, "create: config needs %d B of shared memory per CTA (limit %d)", need, (int)prop.sharedMemPerBlockOptin);
   }
-  if (h->K0 > 64) {
+  if (h->tm_z + h->K0 / 2 > 512) {
     delete h;
-    return set_error(METRPO_ERR_UNSUPPORTED, "create: padded dynamics input %d > 64 (TMEM budget of the Z operand)", h->K0);
+    return set_error(METRPO_ERR_UNSUPPORTED, "create: TMEM budget exceeded (S_pad %d, padded dynamics input %d)", h->S_pad, h->K0);
   }
 
   const size_t rows_pad = static_cast<size_t>(h->n_tiles) * TILE_M;
@@ -243,7 +286,7 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
   };
   alloc(reinterpret_cast<void**>(&h->wstream), h->model_stride * c.n_models);
-  alloc(reinterpret_cast<void**>(&h->bias), static_cast<size_t>(c.n_models) * (2 * c.hidden + 32) * 4);
+  alloc(reinterpret_cast<void**>(&h->bias), static_cast<size_t>(c.n_models) * (2 * c.hidden + BIAS_PAD) * 4);
   alloc(reinterpret_cast<void**>(&h->norm), (2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4);
   alloc(reinterpret_cast<void**>(&h->pol), h->pol_floats * 4);
   alloc(reinterpret_cast<void**>(&h->xbuf), static_cast<size_t>(h->max_slots) * 2 * c.n_models * c.state_dim * TILE_M * 4);
@@ -256,7 +299,8 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   h->dbg_words = DBG_HEADER + h->max_slots * c.n_models * (NUM_THREADS / 32) * DBG_WORDS_PER_WARP;
   alloc(reinterpret_cast<void**>(&h->dbg), h->dbg_words * 4);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    e = h->big ? cudaFuncSetAttribute(rollout_kernel<64, 24, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)
+               : cudaFuncSetAttribute(rollout_kernel<32, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   if (e != cudaSuccess) {
     free_handle(h);
     return set_error(e == cudaErrorMemoryAllocation ? METRPO_ERR_NOMEM : METRPO_ERR_CUDA, "create: %s", cudaGetErrorString(e));
@@ -283,11 +327,11 @@ extern "C" int metrpo_rollout_set_dynamics(metrpo_rollout_t* h, int k, const flo
   const int H = h->cfg.hidden, S = h->cfg.state_dim;
   uint8_t* dst = h->wstream + static_cast<size_t>(k) * h->model_stride;
   const int T = 256;
-  pack_w1_kernel<<<(static_cast<size_t>(H) * H + T - 1) / T, T, 0, st>>>(W1, dst, H, h->KC, h->stage_bytes);
+  pack_w1_kernel<<<(static_cast<size_t>(H) * H + T - 1) / T, T, 0, st>>>(W1, dst, H, h->KC, h->N1, h->stage_bytes);
   pack_w0_kernel<<<(h->K0 * H + T - 1) / T, T, 0, st>>>(W0, b0, dst, H, h->Din, h->K0, h->w0g_bytes,
                                                         h->off_w0g);
-  pack_w2_kernel<<<(H * h->S_pad + T - 1) / T, T, 0, st>>>(W2, dst, H, S, h->S_pad, h->off_w2, h->w2chunk_bytes);
-  pack_bias_kernel<<<(2 * H + 32 + T - 1) / T, T, 0, st>>>(b0, b1, b2, h->bias + static_cast<size_t>(k) * (2 * H + 32), H, S);
+  pack_w2_kernel<<<(H * h->S_pad + T - 1) / T, T, 0, st>>>(W2, dst, H, S, h->S_pad, h->N1, h->off_w2, h->w2chunk_bytes);
+  pack_bias_kernel<<<(2 * H + BIAS_PAD + T - 1) / T, T, 0, st>>>(b0, b1, b2, h->bias + static_cast<size_t>(k) * (2 * H + BIAS_PAD), H, S);
   METRPO_CUDA_OK(cudaGetLastError());
   h->dyn_set[k] = 1;
   return METRPO_OK;
@@ -320,7 +364,7 @@ extern "C" int metrpo_rollout_set_policy(metrpo_rollout_t* h, const float* const
     pack_policy_layer_kernel<<<(n + 255) / 256, 256, 0, st>>>(W[l], b[l], h->pol + L.w_off, h->pol + L.b_off,
                                                               L.nin, L.nout, L.npad);
   }
-  copy_f32_kernel<<<1, 32, 0, st>>>(log_std, h->pol + h->pol_logstd_off, h->cfg.action_dim, 0.f, AMAX);
+  copy_f32_kernel<<<1, 32, 0, st>>>(log_std, h->pol + h->pol_logstd_off, h->cfg.action_dim, 0.f, h->amax);
   METRPO_CUDA_OK(cudaGetLastError());
   h->pol_set = true;
   return METRPO_OK;
@@ -442,7 +486,9 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
   p.K0 = h->K0; p.H = c.hidden; p.S_pad = h->S_pad; p.K = c.n_models;
   if (!p.per_model) p.B = c.n_envs;
   p.T_max = c.max_path_length; p.env_id = c.env_id; p.sam_mode = c.sam_mode;
-  p.NC = h->NC; p.KC = h->KC; p.row_offset = c.row_offset;
+  p.NC = h->NC; p.KC = h->KC; p.N1 = h->N1; p.row_offset = c.row_offset;
+  p.tm_acc0 = h->tm_acc0; p.tm_acc2 = h->tm_acc2; p.tm_h0 = h->tm_h0; p.tm_z = h->tm_z;
+  p.pol_in_smem = h->pol_in_smem;
   p.n_tiles = p.per_model ? (p.B + TILE_M - 1) / TILE_M : h->n_tiles;
   p.wstream = h->wstream; p.model_stride = h->model_stride; p.stage_bytes = h->stage_bytes;
   p.w0g_bytes = h->w0g_bytes; p.w2chunk_bytes = h->w2chunk_bytes; p.off_w2 = h->off_w2;
@@ -465,7 +511,8 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
   METRPO_CUDA_OK(cudaMemsetAsync(h->dbg, 0, h->dbg_words * 4, st));
   void* args[] = {&p};
   // cooperative launch: all gang CTAs must be co-resident (they spin on each other)
-  METRPO_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rollout_kernel),
+  METRPO_CUDA_OK(cudaLaunchCooperativeKernel(h->big ? reinterpret_cast<void*>(rollout_kernel<64, 24, 128>)
+                                                    : reinterpret_cast<void*>(rollout_kernel<32, 8, 256>),
                                              dim3(n_slots * c.n_models), dim3(NUM_THREADS), args,
                                              h->smem_bytes, st));
   h->last_launches = 1;

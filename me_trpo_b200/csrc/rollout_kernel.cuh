@@ -51,20 +51,24 @@ namespace metrpo {
 
 constexpr int TILE_M = 128;
 constexpr int NSTAGE = 4;     // must stay 4: the EMPTY barriers double as H0-buffer-free signals (stage & 1 == chunk & 1)
-constexpr int SMAX = 32;      // max state dim held in registers
-constexpr int AMAX = 8;       // max action dim
-constexpr int HPMAX = 32;     // max policy hidden width
-constexpr int MAX_SEG = 32;   // segments per gang slot
-constexpr int W1_TILE_BYTES = 256 * 64 * 2;   // 32 KB: [256 n][64 k] bf16, SW128
+// The kernel is compiled for two register budgets <SMAX, AMAX> = <32, 8> (every shipped env but
+// humanoid) and <64, 24> (humanoid: S = 55, A = 21, policy 100-50-25); rollout_api.cu picks one.
+constexpr int HPB = 32;       // policy hidden layers are evaluated in blocks of 32 output columns
+constexpr int HPMAX = 128;    // max policy hidden width
+constexpr int MAX_SEG = 128;  // segments per gang slot
+// W1 stage: [N1 n][64 k] bf16, SW128, N1 = 256 (32 KB) or 128 (16 KB; configs whose operands do not
+// fit TMEM / shared memory next to a 256-column layer-1 accumulator)
+constexpr int BIAS_PAD = 64;    // zero-padded b2 slot of the per-model bias blob [b0 | b1 | b2]
 constexpr int NUM_THREADS = 192;
 constexpr int EPI_THREADS = 128;
 
-// TMEM column map (512 allocated)
-constexpr uint32_t TM_ACC1 = 0;      // 256 cols fp32; after the drain: 4 x 32 cols of packed bf16 H1
-constexpr uint32_t TM_ACC0 = 256;    // 128 cols: layer-0 accumulator of one group (2 chunks)
-constexpr uint32_t TM_ACC2 = 384;    // S_pad (<= 32) cols
-constexpr uint32_t TM_H0 = 416;      // 2 x 32 cols: relu(h0) chunk as packed bf16 pairs (A of L1)
-constexpr uint32_t TM_Z = 480;       // K0/2 (<= 32) cols: normalised input as packed bf16 (A of L0)
+// TMEM column map (512 allocated), offsets chosen by the host (KParams::tm_*):
+//   acc1  N1 cols fp32 at 0; after the drain: N1/64 x 32 cols of packed bf16 H1
+//   acc0  128 cols: layer-0 accumulator of one group (2 chunks)
+//   acc2  S_pad cols
+//   H0    2 x 32 cols: relu(h0) chunk as packed bf16 pairs (A of L1)
+//   Z     K0/2 cols: normalised input as packed bf16 (A of L0)
+constexpr uint32_t TM_ACC1 = 0;
 
 enum {
   B_FULL = 0,        // [NSTAGE] W1 stage landed (tx)
@@ -86,14 +90,18 @@ enum {
 // with several waiters rather than one barrier per waiter.
 
 struct PolicyLayer {
-  int nin, nout, npad;   // npad = 32 for hidden layers, 8 for the output layer
+  int nin, nout, npad;   // npad = nout rounded up to 32 for hidden layers, AMAX for the output layer
   int w_off, b_off;      // float offsets into the policy blob
+  int in_off, out_off;   // float offsets of the activation rows [n][128] in the scratch area (a layer
+                         // of <= 32 outputs runs in place, wider ones ping-pong between two regions)
 };
 
 struct KParams {
   // dims
   int S, A, SA, drop, Din, K0, H, S_pad, K, B, T_max, env_id, sam_mode, determ;
-  int NC, KC;
+  int NC, KC, N1;        // layer-1 passes, 64-wide reduction chunks, pass width (256 or 128)
+  uint32_t tm_acc0, tm_acc2, tm_h0, tm_z;   // TMEM column offsets
+  int pol_in_smem;       // policy blob staged in shared memory (else read through L1 from global)
   int n_steps, n_slots, n_tiles;
   int resume;            // 1: state comes from row_state (B1 step / continued run)
   int per_model;         // 1: per-model validation-cost rollout (model_based_rl.py:122-142): every
@@ -106,7 +114,7 @@ struct KParams {
   const uint8_t* wstream;
   unsigned long long model_stride;
   uint32_t stage_bytes, w0g_bytes, w2chunk_bytes, off_w2, off_w0g;   // w0g: [128 n][K0] tile
-  const float* bias;     // [K][2H + 32]: b0 (unused by the kernel) | b1 | b2 (zero padded)
+  const float* bias;     // [K][2H + BIAS_PAD]: b0 (unused by the kernel) | b1 | b2 (zero padded)
   const float* norm;     // in_mean[SA] | in_std[SA] | diff_mean[S] | diff_std[S]
   const float* pol;      // policy blob (padded W, b per layer, then log_std[AMAX])
   int pol_floats, n_pol_layers, pol_out_tanh, pol_logstd_off;
@@ -227,6 +235,7 @@ constexpr int TRACE_CAP = 4096;
 #endif
 
 // per-row analytic cost (reward = -cost); u is the clipped action.  envs/com_*_env.py
+template <int SMAX, int AMAX>
 __device__ __forceinline__ float env_cost(int env_id, int S, int A, const float (&xn)[SMAX],
                                           const float (&u)[AMAX]) {
   float su2 = 0.f;
@@ -261,6 +270,7 @@ __device__ __forceinline__ float env_cost(int env_id, int S, int A, const float 
       return -(xn[7] - 0.01f * 0.5f * su2);
   }
 }
+template <int SMAX>
 __device__ __forceinline__ bool env_is_done(int env_id, int S, const float (&xn)[SMAX]) {
   if (env_id != METRPO_ENV_ANT) return false;   // NeuralNetEnv default (env_helpers.py:537)
   bool finite = true;
@@ -282,31 +292,32 @@ __device__ __forceinline__ void dense_fma_row(float2 (&acc2)[NP / 2], float xi, 
   }
 }
 template <int NP>
-__device__ __forceinline__ void dense_load_row(const float* in_s, const float* W, int i, int r, float& xi,
+__device__ __forceinline__ void dense_load_row(const float* in_s, const float* W, int ld, int i, int r, float& xi,
                                                float4 (&w)[NP / 4]) {
   xi = in_s[i * TILE_M + r];
-  const float4* w4 = reinterpret_cast<const float4*>(W + i * NP);
+  const float4* w4 = reinterpret_cast<const float4*>(W + i * ld);
 #pragma unroll
   for (int j = 0; j < NP / 4; ++j) w[j] = w4[j];
 }
+// NP output columns starting at W (row stride ld floats), b
 template <int NP>
-__device__ __forceinline__ void dense_layer(const float* in_s, int nin, const float* W,
+__device__ __forceinline__ void dense_layer(const float* in_s, int nin, const float* W, int ld,
                                             const float* b, float (&acc)[NP], int r) {
   float2 acc2[NP / 2];
 #pragma unroll
   for (int j = 0; j < NP / 2; ++j) acc2[j] = make_float2(b[2 * j], b[2 * j + 1]);
   float4 wa[NP / 4], wb[NP / 4];
   float xa, xb;
-  dense_load_row<NP>(in_s, W, 0, r, xa, wa);
+  dense_load_row<NP>(in_s, W, ld, 0, r, xa, wa);
   int i = 0;
   for (; i + 2 < nin; i += 2) {          // weight rows i+1 / i+2 are in flight while row i / i+1 is used
-    dense_load_row<NP>(in_s, W, i + 1, r, xb, wb);
+    dense_load_row<NP>(in_s, W, ld, i + 1, r, xb, wb);
     dense_fma_row<NP>(acc2, xa, wa);
-    dense_load_row<NP>(in_s, W, i + 2, r, xa, wa);
+    dense_load_row<NP>(in_s, W, ld, i + 2, r, xa, wa);
     dense_fma_row<NP>(acc2, xb, wb);
   }
   if (i + 1 < nin) {
-    dense_load_row<NP>(in_s, W, i + 1, r, xb, wb);
+    dense_load_row<NP>(in_s, W, ld, i + 1, r, xb, wb);
     dense_fma_row<NP>(acc2, xa, wa);
     dense_fma_row<NP>(acc2, xb, wb);
   } else {
@@ -347,6 +358,7 @@ __device__ __forceinline__ float fast_tanh(float x) {
 }
 
 // =============================================================================================
+template <int SMAX, int AMAX, int N1>
 __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -362,7 +374,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
   float* sScr = reinterpret_cast<float*>(smem + p.off_scr);   // [max(S+A,32)][128] fp32 scratch
   float* sBias = reinterpret_cast<float*>(smem + p.off_sbias);
   float* sNorm = reinterpret_cast<float*>(smem + p.off_snorm);
-  float* sPol = reinterpret_cast<float*>(smem + p.off_spol);
+  // the narrow instantiation always stages the policy blob in shared memory (<= 16 KB); the wide one
+  // reads it through L1 from global when it does not fit next to the activations
+  float* sPolS = reinterpret_cast<float*>(smem + p.off_spol);
+  const float* sPol = (SMAX <= 32 || p.pol_in_smem) ? sPolS : p.pol;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
 
   const int NCH = p.NC * p.KC;          // chunks per step
@@ -396,13 +411,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
   {  // constants -> smem (generic loads; read-only for the rest of the kernel)
-    const float* gb = p.bias + static_cast<size_t>(k) * (2 * p.H + 32);
-    for (int i = tid; i < 2 * p.H + 32; i += NUM_THREADS) sBias[i] = gb[i];
+    const float* gb = p.bias + static_cast<size_t>(k) * (2 * p.H + BIAS_PAD);
+    for (int i = tid; i < 2 * p.H + BIAS_PAD; i += NUM_THREADS) sBias[i] = gb[i];
     for (int i = tid; i < 2 * p.SA + 2 * p.S; i += NUM_THREADS) {
       const float v = p.norm[i];
       sNorm[i] = (i >= p.SA && i < 2 * p.SA) ? __frcp_rn(v) : v;   // in_std slot holds 1 / in_std
     }
-    for (int i = tid; i < p.pol_floats; i += NUM_THREADS) sPol[i] = p.pol[i];
+    if (SMAX <= 32 || p.pol_in_smem)
+      for (int i = tid; i < p.pol_floats; i += NUM_THREADS) sPolS[i] = p.pol[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -468,10 +484,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
       // chunk's MMAs are still queued.
       {
         const uint32_t idesc0 = idesc_bf16_f32(128, 128);
-        const uint32_t idesc1 = idesc_bf16_f32(128, 256);
+        const uint32_t idesc1 = idesc_bf16_f32(128, N1);
         const uint32_t idesc2 = idesc_bf16_f32(128, p.S_pad);
         const int k0steps = p.K0 / 16;
-        const uint32_t ztm = tmem + TM_Z;                    // A of L0: 8 TMEM columns per 16-k step
+        const uint32_t ztm = tmem + p.tm_z;                    // A of L0: 8 TMEM columns per 16-k step
         const uint32_t w0_kstep = (2 * 128 * 16) >> 4;       // W0 group tile: [128 n][K0] no-swizzle
         const uint64_t w0desc0 = smem_desc_noswz(smem_u32(sW0g), 128 * 16, 128);
         const uint32_t w0slot = p.w0g_bytes >> 4;
@@ -479,7 +495,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
         const uint32_t w2_sub = (p.S_pad * 128) >> 4;
         const uint64_t stdesc0 = smem_desc_sw128(smem_u32(sStage));
         const uint32_t ststride = p.stage_bytes >> 4;
-        const uint32_t acc0 = tmem + TM_ACC0, acc1 = tmem + TM_ACC1, acc2 = tmem + TM_ACC2;
+        const uint32_t acc0 = tmem + p.tm_acc0, acc1 = tmem + TM_ACC1, acc2 = tmem + p.tm_acc2;
+        constexpr int nsl = N1 / 64;   // 64-column slices of a layer-1 pass
 
 #define WAITW1(idx, par)                                                                      \
   do {                                                                                        \
@@ -558,7 +575,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                   umma_ts(acc0, ztm + j * 8, w0desc0 + (gg & 1) * w0slot + j * w0_kstep, idesc0, j > 0);
                 umma_commit(&bars[B_ACC0FULL + (gg & 1)]);
               }
-              const uint32_t at = tmem + TM_H0;
+              const uint32_t at = tmem + p.tm_h0;
               const uint64_t bd = stdesc0 + s * ststride;
               umma_ts(acc1, at, bd, idesc1, first_of_pass ? 0u : 1u);
               umma_ts(acc1, at + 8, bd + 2, idesc1, 1);
@@ -576,7 +593,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
             TRACE(1, 0x300 | (2 * G));
             tc_fence_after();
             if (elect_one()) {
-              const uint32_t at = tmem + TM_H0 + 32;
+              const uint32_t at = tmem + p.tm_h0 + 32;
               const uint64_t bd = stdesc0 + s1 * ststride;
               umma_ts(acc1, at, bd, idesc1, 1);
               umma_ts(acc1, at + 8, bd + 2, idesc1, 1);
@@ -589,7 +606,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                    need_l0_2 ? B_ACC0FREE : -1, (gg - 1) & 1,
                    need_l0_2 ? B_W0FULL + (int)(gg & 1) : -1, (gg >> 1) & 1);
             if (elect_one()) {
-              const uint32_t at = tmem + TM_H0 + 32;
+              const uint32_t at = tmem + p.tm_h0 + 32;
               const uint64_t bd = stdesc0 + s1 * ststride;
               umma_ts(acc1, at + 16, bd + 4, idesc1, 1);
               umma_ts(acc1, at + 24, bd + 6, idesc1, 1);
@@ -608,7 +625,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               WAITW2(B_H1FULL + 0, npass & 1, B_W2FULL, w2n & 1); ++w2n;
               TRACE(1, 0x2200 | (nc << 4));
 #pragma unroll 1
-              for (int sub = 0; sub < 4; ++sub) {
+              for (int sub = 0; sub < nsl; ++sub) {
                 if (sub > 0) WAITW1(B_H1FULL + sub, npass & 1);
                 tc_fence_after();
                 if (elect_one()) {
@@ -726,23 +743,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               a_mean[i] = a_raw[i];
             }
           } else {
-            // policy mean network (training.py:99-103), fp32 on CUDA cores, in place in scrA
+            // policy mean network (training.py:99-103), fp32 on CUDA cores.  Activations live in
+            // the thread's own column of the scratch rows.
+            if constexpr (SMAX <= 32) {
+              // narrow policies (hidden <= 32): every layer in place, compile-time row stride
 #pragma unroll
-            for (int s = 0; s < SMAX; ++s)
-              if (s < S) scrA[s * TILE_M + r] = x[s];
-            for (int l = 0; l < p.n_pol_layers; ++l) {
-              const PolicyLayer L = p.pl[l];
-              const bool last = (l == p.n_pol_layers - 1);
-              if (!last) {
-                float acc[HPMAX];
-                dense_layer<HPMAX>(scrA, L.nin, sPol + L.w_off, sPol + L.b_off, acc, r);
+              for (int s = 0; s < SMAX; ++s)
+                if (s < S) scrA[s * TILE_M + r] = x[s];
+              for (int l = 0; l < p.n_pol_layers; ++l) {
+                const PolicyLayer L = p.pl[l];
+                const bool last = (l == p.n_pol_layers - 1);
+                if (!last) {
+                  float acc[HPB];
+                  dense_layer<HPB>(scrA, L.nin, sPol + L.w_off, HPB, sPol + L.b_off, acc, r);
 #pragma unroll
-                for (int j = 0; j < HPMAX; ++j) scrA[j * TILE_M + r] = fast_tanh(acc[j]);
-              } else {
-                float acc[AMAX];
-                dense_layer<AMAX>(scrA, L.nin, sPol + L.w_off, sPol + L.b_off, acc, r);
+                  for (int j = 0; j < HPB; ++j) scrA[j * TILE_M + r] = fast_tanh(acc[j]);
+                } else {
+                  float acc[AMAX];
+                  dense_layer<AMAX>(scrA, L.nin, sPol + L.w_off, AMAX, sPol + L.b_off, acc, r);
 #pragma unroll
-                for (int i = 0; i < AMAX; ++i) a_mean[i] = p.pol_out_tanh ? tanhf(acc[i]) : acc[i];
+                  for (int i = 0; i < AMAX; ++i) a_mean[i] = p.pol_out_tanh ? tanhf(acc[i]) : acc[i];
+                }
+              }
+            } else {
+              // wide policies: hidden layers in blocks of 32 output columns (one block: in place;
+              // wider: ping-pong between two scratch regions, see PolicyLayer)
+#pragma unroll
+              for (int s = 0; s < SMAX; ++s)
+                if (s < S) scrA[p.pl[0].in_off + s * TILE_M + r] = x[s];
+              for (int l = 0; l < p.n_pol_layers; ++l) {
+                const PolicyLayer& L = p.pl[l];
+                const bool last = (l == p.n_pol_layers - 1);
+                if (!last) {
+#pragma unroll 1
+                  for (int j0 = 0; j0 < L.nout; j0 += HPB) {
+                    float acc[HPB];
+                    dense_layer<HPB>(scrA + L.in_off, L.nin, sPol + L.w_off + j0, L.npad, sPol + L.b_off + j0, acc, r);
+#pragma unroll
+                    for (int j = 0; j < HPB; ++j)
+                      if (j0 + j < L.nout) scrA[L.out_off + (j0 + j) * TILE_M + r] = fast_tanh(acc[j]);
+                  }
+                } else {
+                  float acc[AMAX];
+                  dense_layer<AMAX>(scrA + L.in_off, L.nin, sPol + L.w_off, L.npad, sPol + L.b_off, acc, r);
+#pragma unroll
+                  for (int i = 0; i < AMAX; ++i) a_mean[i] = p.pol_out_tanh ? tanhf(acc[i]) : acc[i];
+                }
               }
             }
             TRACE(2, 0x1010);
@@ -782,7 +828,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               const float z1 = f1 < p.Din ? scrA[(f1 + p.drop) * TILE_M + r] : (f1 < p.Din + 2 ? 1.f : 0.f);
               pk[i] = pack_bf16x2(z0, z1);
             }
-            tmem_st8(tmem + lane_base + TM_Z + c * 8, pk);
+            tmem_st8(tmem + lane_base + p.tm_z + c * 8, pk);
           }
           tmem_st_wait();
           tc_fence_before();
@@ -801,10 +847,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                 WAITB(B_ACC0FULL + (gg & 1), (gg >> 1) & 1);
                 TRACE(2, 0x200 | (2 * G));
                 tc_fence_after();
-                tmem_ld32(tmem + lane_base + TM_ACC0, v0);
-                tmem_ld32(tmem + lane_base + TM_ACC0 + 32, v1);
-                tmem_ld32(tmem + lane_base + TM_ACC0 + 64, v2);
-                tmem_ld32(tmem + lane_base + TM_ACC0 + 96, v3);
+                tmem_ld32(tmem + lane_base + p.tm_acc0, v0);
+                tmem_ld32(tmem + lane_base + p.tm_acc0 + 32, v1);
+                tmem_ld32(tmem + lane_base + p.tm_acc0 + 64, v2);
+                tmem_ld32(tmem + lane_base + p.tm_acc0 + 96, v3);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[B_ACC0FREE]);        // next group's L0 may overwrite acc0
@@ -813,13 +859,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                 relu_pack<false>(v2, v3, nullptr, pk2);
                 // H0 buffer 0 is free once L1 of chunk 2*gg-2 completed (its stage's EMPTY barrier)
                 if (gg >= 1) WAITB(B_EMPTY + ((2 * gg - 2) & 3), ((2 * gg - 2) >> 2) & 1);
-                tmem_st32(tmem + lane_base + TM_H0, pk);
+                tmem_st32(tmem + lane_base + p.tm_h0, pk);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[B_H0FULL + 0]);
                 TRACE(2, 0x400 | (2 * G));
                 if (gg >= 1) WAITB(B_EMPTY + ((2 * gg - 1) & 3), ((2 * gg - 1) >> 2) & 1);
-                tmem_st32(tmem + lane_base + TM_H0 + 32, pk2);
+                tmem_st32(tmem + lane_base + p.tm_h0 + 32, pk2);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[B_H0FULL + 1]);
@@ -843,11 +889,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                   // converted and stored (slices touch disjoint columns)
                   uint32_t va0[32], va1[32], vb0[32], vb1[32], pk[32];
                   const uint32_t a1 = tmem + lane_base + TM_ACC1;
-                  const float* bb = sB1 + drain_nc * 256;
+                  const float* bb = sB1 + drain_nc * N1;
+                  constexpr int nsl = N1 / 64;
                   tmem_ld32(a1, va0);
                   tmem_ld32(a1 + 32, va1);
                   tmem_ld_wait();
-#define DRAIN_SLICE(sub, cur0, cur1, nxt0, nxt1, has_next)                                    \
+#define DRAIN_SLICE(sub, cur0, cur1, nxt0, nxt1, has_next_)                                   \
+                  if ((sub) < nsl) {                                                          \
+                  const bool has_next = (has_next_) && (sub) + 1 < nsl;                       \
                   if (has_next) {                                                             \
                     tmem_ld32(a1 + ((sub) + 1) * 64, nxt0);                                   \
                     tmem_ld32(a1 + ((sub) + 1) * 64 + 32, nxt1);                              \
@@ -858,7 +907,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                   tmem_st_wait();                                                             \
                   tc_fence_before();                                                          \
                   mbar_arrive(&bars[B_H1FULL + (sub)]);                                       \
-                  if (has_next) tmem_ld_wait();
+                  if (has_next) tmem_ld_wait();                                               \
+                  }
                   DRAIN_SLICE(0, va0, va1, vb0, vb1, true)
                   DRAIN_SLICE(1, vb0, vb1, va0, va1, true)
                   DRAIN_SLICE(2, va0, va1, vb0, vb1, true)
@@ -874,18 +924,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           // ================= finish step: candidate, exchange, select, reward, reset =========
           float cand[SMAX];
           {
-            uint32_t v[32];
             TRACE(2, 0x1002);
             WAITB(B_ACC2FULL, a2n & 1); ++a2n;
             TRACE(2, 0x1003);
             tc_fence_after();
-            tmem_ld32(tmem + lane_base + TM_ACC2, v);
-            tmem_ld_wait();
 #pragma unroll
-            for (int s = 0; s < SMAX; ++s) {
-              const float o = __fadd_rn(__uint_as_float(v[s]), sB2[s]);
-              // tf.add(diff_mean + diff_std * nn_output, x)   (training.py:257)
-              cand[s] = (s < S) ? __fadd_rn(__fadd_rn(dMean[s], __fmul_rn(dStd[s], o)), x[s]) : 0.f;
+            for (int c = 0; c < SMAX / 32; ++c) {
+              uint32_t v[32];
+              if (32 * c < p.S_pad) {     // warp-uniform
+                tmem_ld32(tmem + lane_base + p.tm_acc2 + 32 * c, v);
+                tmem_ld_wait();
+              }
+#pragma unroll
+              for (int q = 0; q < 32; ++q) {
+                const int s = 32 * c + q;
+                if (s < S) {
+                  const float o = __fadd_rn(__uint_as_float(v[q]), sB2[s]);
+                  // tf.add(diff_mean + diff_std * nn_output, x)   (training.py:257)
+                  cand[s] = __fadd_rn(__fadd_rn(dMean[s], __fmul_rn(dStd[s], o)), x[s]);
+                } else {
+                  cand[s] = 0.f;
+                }
+              }
             }
           }
           float xnext[SMAX];
@@ -1000,7 +1060,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           float u[AMAX];
 #pragma unroll
           for (int i = 0; i < AMAX; ++i) u[i] = fminf(fmaxf(a_raw[i], -1.f), 1.f);
-          const float reward = -env_cost(p.env_id, S, A, xnext, u);
+          const float reward = -env_cost<SMAX, AMAX>(p.env_id, S, A, xnext, u);
           if (p.per_model) {
             // _policy_cost += gamma**t * cost_tf(x, u, x_next[, dones]); dones = max(dones,
             // is_done_tf(x, x_next)) AFTER the cost (model_based_rl.py:133-139; Ant masks the cost
@@ -1008,13 +1068,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
             const float c = __fmul_rn(-reward, 1.f - pm_dmask);
             pm_acc = __fadd_rn(pm_acc, __fmul_rn(pm_gpow, c));
             pm_gpow = __fmul_rn(pm_gpow, p.gamma);
-            if (env_is_done(p.env_id, S, xnext)) pm_dmask = 1.f;
+            if (env_is_done<SMAX>(p.env_id, S, xnext)) pm_dmask = 1.f;
 #pragma unroll
             for (int s = 0; s < SMAX; ++s) x[s] = xnext[s];
             continue;
           }
           ts += 1;
-          const bool dn = env_is_done(p.env_id, S, xnext) || (ts >= p.T_max);   // :603-604
+          const bool dn = env_is_done<SMAX>(p.env_id, S, xnext) || (ts >= p.T_max);   // :603-604
           if (k == 0 && valid) {
             const size_t o = static_cast<size_t>(t) * p.B + row;
             if (K == 1) {   // (with K > 1 these were stored while waiting for the exchange)

@@ -35,7 +35,9 @@ def _cfg(lib, **kw):
     (dict(env_id=9), -1, "env_id"),
     (dict(sam_mode=7), -1, "sam_mode"),
     (dict(hidden=300), -3, "multiple of 256"),
-    (dict(state_dim=55, action_dim=21, policy_dims=[55, 32, 32, 21]), -3, "S <= 32"),
+    (dict(state_dim=70, action_dim=21, policy_dims=[70, 32, 32, 21]), -3, "S <= 64"),
+    (dict(state_dim=55, action_dim=21, hidden=192, policy_dims=[55, 32, 32, 21]), -3, "multiple of 128"),
+    (dict(policy_dims=[18, 200, 32, 6]), -3, "policy hidden width"),
     (dict(precision=3), -3, "PREC_BF16"),
     (dict(policy_dims=[17, 32, 32, 6]), -1, "policy_dims"),
     (dict(env_id=3, state_dim=10, action_dim=2, policy_dims=[10, 32, 32, 2]), -1, "needs state_dim"),
@@ -76,8 +78,8 @@ def test_null_handles_are_errors_not_crashes(metrpo_lib):
 
 def _schedule(metrpo_lib, n_tiles, n_slots, T):
     lib = metrpo_lib.load()
-    buf = np.full(n_slots * 64 * 4, -7, np.int32)
-    ms = lib.metrpo_debug_schedule(n_tiles, n_slots, T, buf.ctypes.data_as(ctypes.c_void_p), n_slots * 64)
+    buf = np.full(n_slots * 256 * 4, -7, np.int32)
+    ms = lib.metrpo_debug_schedule(n_tiles, n_slots, T, buf.ctypes.data_as(ctypes.c_void_p), n_slots * 256)
     assert ms > 0, metrpo_lib.last_error()
     return buf[:n_slots * ms * 4].reshape(n_slots, ms, 4)
 

@@ -94,6 +94,7 @@ PM_CASES = [
     ("hc_rows_lt_envs", "half-cheetah", 5, 130, 1024, 6, 256, 0.97),
     ("ant_mask", "ant", 4, 256, 256, 6, 256, 0.99),
     ("hopper_k1", "hopper", 1, 64, 64, 5, 256, 1.0),
+    ("humanoid", "humanoid", 3, 200, 256, 4, 128, 0.99),
     ("swimmer_many_tiles", "swimmer", 5, 4096, 4096, 3, 256, 1.0),   # 32 tiles > 29 slots: 2 tiles on some slots
 ]
 

@@ -62,6 +62,10 @@ BIG = [
     ("ant_b256", "ant", 4, 256, 5, 100, 256, "step_rand", "explicit"),
     ("hc_split_chains", "half-cheetah", 5, 4096, 12, 100, 256, "step_rand", "philox"),
     ("hc_k1", "half-cheetah", 1, 128, 3, 100, 256, "one_model", "explicit"),
+    # humanoid dims: S=55, A=21, policy 100-50-25 -> the <64,24,128> instantiation (128-column passes)
+    ("humanoid_b200", "humanoid", 3, 200, 5, 3, 256, "step_rand", "explicit"),
+    ("humanoid_k20_philox", "humanoid", 20, 1100, 4, 100, 128, "step_rand", "philox"),
+    ("humanoid_mean_std", "humanoid", 3, 128, 3, 100, 128, "model_mean_std", "explicit"),
 ]
 
 
