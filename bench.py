@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENV, K_MODELS, B_ROWS, HORIZON, HIDDEN = "half-cheetah", 5, 4096, 1000, 1024
+E2E_CHUNKS = 8
 METRIC = "simulated env steps/sec (ensemble x batch x horizon)"
 UNIT = "units/s"
 
@@ -170,9 +171,10 @@ def run_cuda(args, rank, local_rank, world):
         if e2e:                                         # host buffers in, host buffers out
             a = init_h.to(dev, non_blocking=True)
             b = pool_h.to(dev, non_blocking=True)
-            ro.run(T, a, b, seed=1, offset=i * T, out=out)
-            for k2, v in out.items():
-                host_out[k2].copy_(v, non_blocking=True)
+            # public API of the host-side sampler: chunked launches with the D2H copy of finished
+            # steps overlapped with the rest of the horizon; returns after queuing, the end event
+            # below covers the last copy
+            ro.run_to_host(T, a, b, host_out=host_out, dev_out=out, seed=1, offset=i * T, n_chunks=E2E_CHUNKS)
         else:
             ro.run(T, init_d, pool_d, seed=1, offset=i * T, out=out)
         e1.record()
@@ -197,7 +199,7 @@ def run_cuda(args, rank, local_rank, world):
 
     total_ms, per_step, clocks = timed(False)
     total_ms_e2e, _, _ = timed(True)
-    finite = bool(torch.isfinite(out["obs"]).all().item())
+    finite = bool(torch.isfinite(out["obs"]).all().item()) and bool(torch.isfinite(host_out["obs"]).all().item())
 
     units_per_step = K_MODELS * B_ROWS * T * world
     value = units_per_step * args.steps / (total_ms * 1e-3)
@@ -236,8 +238,10 @@ def run_cuda(args, rank, local_rank, world):
                              "sample": "40 of 1000 env-steps of the same workload (homogeneous steps), NumPy fp32, "
                                        "all BLAS threads, reference-faithful loop; %.1f s" % cpu_dt},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "pinned host init/reset states -> device, fused rollout, whole trajectory "
-                            "(obs, act, mean, rew, done) -> pinned host"},
+                    "gpu_launches_per_step": E2E_CHUNKS,
+                    "what": "pinned host init/reset states -> device, fused rollout in %d chained launches, whole "
+                            "trajectory (obs, act, mean, rew, done) -> pinned host, copy of finished steps "
+                            "overlapped with the remaining horizon (EnsembleRollout.run_to_host)" % E2E_CHUNKS},
             "gpu_launches": args.steps * ro.last_launches(),
             "clocks": clocks, "finite": finite,
         }

@@ -149,6 +149,16 @@ int metrpo_rollout_run(metrpo_rollout_t* h, int n_steps, const float* init_state
                        uint64_t offset, int determ, float* obs, float* act, float* mean,
                        float* rew, uint8_t* done, float* final_states, void* stream);
 
+/* Continue the rollout of metrpo_rollout_run (or of reset() / step()) for n_steps more steps from
+ * the row state the previous launch left behind (observations, time-in-path, resets consumed);
+ * identical to one longer run() when `offset` (global step index of the first step: keys the
+ * Philox streams) and the eps / model_idx / std_noise / output pointers are advanced by the caller.
+ * Lets a host overlap the device->host copy of finished steps with the remaining horizon. */
+int metrpo_rollout_continue(metrpo_rollout_t* h, int n_steps, const float* reset_pool, int R,
+                            const float* eps, const int32_t* model_idx, const float* std_noise,
+                            uint64_t seed, uint64_t offset, int determ, float* obs, float* act,
+                            float* mean, float* rew, uint8_t* done, float* final_states, void* stream);
+
 /* Per-model validation cost of the current policy, the `policy_costs` tensors of
  * build_policy_graph (model_based_rl.py:122-142) that optimize_policy evaluates every log_every
  * iterations on the fixed validation initial states (:1237-1248) to feed the stop criterion

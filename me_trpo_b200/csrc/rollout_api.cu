@@ -541,6 +541,26 @@ extern "C" int metrpo_rollout_run(metrpo_rollout_t* h, int n_steps, const float*
   return rc;
 }
 
+extern "C" int metrpo_rollout_continue(metrpo_rollout_t* h, int n_steps, const float* reset_pool, int R,
+                                       const float* eps, const int32_t* model_idx, const float* std_noise,
+                                       uint64_t seed, uint64_t offset, int determ, float* obs, float* act,
+                                       float* mean, float* rew, uint8_t* done, float* final_states,
+                                       void* stream_) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "continue: null handle");
+  if (n_steps < 1) return set_error(METRPO_ERR_INVALID, "continue: n_steps must be >= 1");
+  if (!reset_pool || R < 1) return set_error(METRPO_ERR_INVALID, "continue: a reset pool with R >= 1 states is required");
+  if (!h->pol_set) return set_error(METRPO_ERR_STATE, "continue: policy was never set");
+  if (!h->state_set) return set_error(METRPO_ERR_STATE, "continue: no row state yet (call run() or reset() first)");
+  METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
+  KParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n_steps = n_steps; p.resume = 1; p.determ = determ ? 1 : 0;
+  p.reset_pool = reset_pool; p.R = R; p.eps = eps; p.model_idx = model_idx;
+  p.std_noise = std_noise; p.seed = seed; p.offset = offset;
+  p.obs = obs; p.act = act; p.mean = mean; p.rew = rew; p.done = done; p.final_states = final_states;
+  return launch(h, p, static_cast<cudaStream_t>(stream_));
+}
+
 extern "C" int metrpo_rollout_model_costs(metrpo_rollout_t* h, int n_steps, int n_rows,
                                           const float* init_states, double gamma, float* row_costs,
                                           float* model_costs, void* stream_) {

@@ -68,6 +68,8 @@ _PROTOS = {
     "metrpo_rollout_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "metrpo_rollout_run": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _u64, _u64, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "metrpo_rollout_continue": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _u64, _u64, _i,
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "metrpo_rollout_model_costs": (_i, [_vp, _i, _i, _vp, _d, _vp, _vp, _vp]),
     "metrpo_rollout_last_launches": (_i, [_vp]),
     "metrpo_rollout_status": (_i, [_vp, _vp]),

@@ -167,6 +167,59 @@ class EnsembleRollout:
         self._keep = self._keep[-8:] + [(init, pool, ep, mi, sn)]
         return out
 
+    def run_to_host(self, n_steps, init_states, reset_pool, host_out=None, dev_out=None, n_chunks=8,
+                    eps=None, model_idx=None, std_noise=None, seed=0, offset=0, determ=False,
+                    want=("obs", "act", "mean", "rew", "done")):
+        """run() whose trajectory lands in pinned HOST buffers: the horizon is cut into n_chunks
+        launches (metrpo_rollout_continue) and the device->host copy of chunk c runs on a second
+        stream while chunk c+1 is computed, so only the last chunk's copy is exposed.  Results are
+        identical to run().  Returns (host_out, dev_out); host buffers are valid after
+        `synchronize()`."""
+        dev, T, B, S, A = self.device, int(n_steps), self.B, self.S, self.A
+        init = _f32(init_states, dev)
+        pool = _f32(reset_pool, dev)
+        ep = None if eps is None else _f32(eps, dev)
+        mi = None if model_idx is None else torch.as_tensor(model_idx, dtype=torch.int32).to(dev).contiguous()
+        sn = None if std_noise is None else _f32(std_noise, dev)
+        shapes = dict(obs=(T, B, S), act=(T, B, A), mean=(T, B, A), rew=(T, B), done=(T, B))
+        dev_out = {} if dev_out is None else dev_out
+        host_out = {} if host_out is None else host_out
+        for name in list(want) + ["final_states"]:
+            shp = (B, S) if name == "final_states" else shapes[name]
+            dt = torch.uint8 if name == "done" else torch.float32
+            if name not in dev_out:
+                dev_out[name] = torch.empty(shp, dtype=dt, device=dev)
+            if name not in host_out:
+                host_out[name] = torch.empty(shp, dtype=dt).pin_memory()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        main, side = torch.cuda.current_stream(dev), self._copy_stream
+        side.wait_stream(main)          # earlier copies out of dev_out / into host_out are ordered
+        n_chunks = max(1, min(int(n_chunks), T))
+        bounds = [round(i * T / n_chunks) for i in range(n_chunks + 1)]
+        sl = lambda t, a, b: None if t is None else t[a:b]
+        for c in range(n_chunks):
+            t0, t1 = bounds[c], bounds[c + 1]
+            g = lambda n: _lib.ptr(dev_out[n][t0:t1]) if n in want else None
+            common = (_lib.ptr(pool), int(pool.shape[0]), _lib.ptr(sl(ep, t0, t1)), _lib.ptr(sl(mi, t0, t1)),
+                      _lib.ptr(sl(sn, t0, t1)), int(seed), int(offset) + t0, 1 if determ else 0, g("obs"), g("act"),
+                      g("mean"), g("rew"), g("done"), _lib.ptr(dev_out["final_states"]), _lib.stream_ptr(main))
+            if c == 0:
+                _lib.check(self._lib.metrpo_rollout_run(self._h, t1 - t0, _lib.ptr(init), *common), "run")
+            else:
+                _lib.check(self._lib.metrpo_rollout_continue(self._h, t1 - t0, *common), "continue")
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                for n in want:
+                    host_out[n][t0:t1].copy_(dev_out[n][t0:t1], non_blocking=True)
+                if c == n_chunks - 1:
+                    host_out["final_states"].copy_(dev_out["final_states"], non_blocking=True)
+        main.wait_stream(side)          # later work on the main stream sees the copies complete
+        self._keep = self._keep[-8:] + [(init, pool, ep, mi, sn)]
+        return host_out, dev_out
+
     # -- R12: per-model validation cost (build_policy_graph, model_based_rl.py:122-142) --------
     def model_costs(self, n_steps, init_states, gamma=1.0, return_rows=False):
         """[K] discounted cost of the deterministic policy under each model rolled forward on its

@@ -69,11 +69,23 @@ class VectorizedSampler(BaseSampler):
         return out
 
     def obtain_samples(self, itr, determ=False):
-        flat = self.obtain_samples_flat(itr, determ)
+        """The reference's contract (list of completed path dicts on the HOST).  The device->host
+        copy of the trajectory is overlapped with the rollout itself (EnsembleRollout.run_to_host)."""
+        algo, env, pol = self.algo, self.algo.env, self.algo.policy
+        B = self._n_envs
+        T = int(self._steps_for_batch())
+        self.rollout.set_policy(pol.W, pol.b, pol.log_std)
+        n_resets = -(-T // algo.max_path_length)
+        R = int(self.reset_pool_size or B * n_resets)
+        init = np.asarray(env.reset_sampler(B), np.float32)          # the initial reset() (:49)
+        pool = np.asarray(env.reset_sampler(R), np.float32)
+        host, self._dev_out = self.rollout.run_to_host(T, init, pool, seed=self.seed,
+                                                       offset=self._calls * (1 << 20), determ=determ,
+                                                       n_chunks=max(1, min(8, T // 32)))
+        self._calls += 1
         self.rollout.synchronize()
         log_std = self.algo.policy.log_std.clamp(min=float(np.log(1e-6))).cpu().numpy()
-        host = {k: v.cpu().numpy() for k, v in flat.items()}
-        return paths_from_flat(host, log_std)
+        return paths_from_flat({k: v.numpy() for k, v in host.items()}, log_std)
 
 
 def paths_from_flat(flat, log_std):

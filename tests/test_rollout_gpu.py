@@ -199,3 +199,25 @@ def test_call_order_errors():
     ro.close()
     with pytest.raises(AssertionError):
         EnsembleRollout("half-cheetah", 2, 128, 10, sam_mode="bogus")
+
+
+@pytest.mark.parametrize("n_chunks", [1, 3, 8])
+def test_run_to_host_chunked_equals_single_launch(n_chunks):
+    """metrpo_rollout_continue: a horizon cut into chained launches (with the D2H copy overlapped)
+    reproduces the single launch bit for bit -- resets inside and across chunk boundaries, chains
+    split across gang slots, Philox noise keyed by global step."""
+    from me_trpo_b200.rollout import EnsembleRollout
+    env, K, B, T, T_max, hidden = "half-cheetah", 5, 4096, 24, 7, 256
+    inp = mg.make_inputs(env, K, B, 1, hidden)
+    ro = EnsembleRollout(env, K, B, T_max, hidden=hidden)
+    ro.set_dynamics_ensemble(inp["models"])
+    ro.set_normalization(**inp["norm"])
+    ro.set_policy(inp["pol"]["W"], inp["pol"]["b"], inp["pol"]["log_std"])
+    ref = {k: v.cpu().numpy() for k, v in ro.run(T, inp["init"], inp["pool"], seed=3, offset=11).items()}
+    ro.synchronize()
+    host, _ = ro.run_to_host(T, inp["init"], inp["pool"], seed=3, offset=11, n_chunks=n_chunks)
+    ro.synchronize()
+    for k in ref:
+        np.testing.assert_array_equal(host[k].numpy(), ref[k], err_msg=k)
+    assert ref["done"].sum() == B * (T // T_max)
+    ro.close()
