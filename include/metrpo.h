@@ -204,6 +204,11 @@ int metrpo_debug_schedule(int n_tiles, int n_slots, int T, int32_t* out, int out
 int metrpo_bench_mma(int ts_mode, int N, int reps, int two_acc, int a_col, int d_col,
                      int wait_each, unsigned long long* out_dev, void* stream);
 
+/* Dev tool: legacy warp-level tensor path (mma.sync) micro-benchmark.  `warps` warps of one CTA
+ * issue reps x 8 independent MMAs each; kind 0: m16n8k8 tf32, 1: m16n8k16 bf16.  out_dev[0] =
+ * clock64 span of warp 0. */
+int metrpo_bench_mma_sync(int kind, int warps, int reps, unsigned long long* out_dev, void* stream);
+
 /* =============================================================================================
  * TRPO half of the inner iteration: sample processing + natural-gradient policy update.
  * All buffers are DEVICE pointers unless marked host; sample index n = t * B + b (the time-major
@@ -228,6 +233,16 @@ typedef int (*metrpo_allreduce_fn)(void* user, double* dev_buf, int n, void* str
 int metrpo_trpo_create(const metrpo_trpo_cfg* cfg, metrpo_trpo_t** out);
 int metrpo_trpo_destroy(metrpo_trpo_t* h);
 int metrpo_trpo_set_allreduce(metrpo_trpo_t* h, metrpo_allreduce_fn fn, void* user);
+/* Implementation of the per-sample pass (loss / gradient / Fisher-vector product):
+ *   AUTO    the fastest measured one for the shape -- today SIMT (the legacy
+ *           warp-level mma.sync path of sm_100a runs TF32 at only 2x the FP32 FMA rate)
+ *   SIMT    fp32 FMA on CUDA cores (any shape)
+ *   TF32    warp-level tensor-core MMAs, single TF32 products (10-bit operand mantissa); policies
+ *           with <= 3 weight layers of width <= 32 (all shipped params/*.json but humanoid)
+ *   TF32X3  same with 3xTF32 split products (fp32-equivalent accuracy) */
+enum { METRPO_TRPO_PASS_AUTO = 0, METRPO_TRPO_PASS_SIMT = 1, METRPO_TRPO_PASS_TF32 = 2,
+       METRPO_TRPO_PASS_TF32X3 = 3 };
+int metrpo_trpo_set_pass_impl(metrpo_trpo_t* h, int impl);
 /* length P of the flat parameter vector, rllab get_params(trainable=True) order:
  * W0[in,out], b0, W1, b1, .., log_std[A]   */
 int metrpo_trpo_num_params(const metrpo_trpo_t* h);

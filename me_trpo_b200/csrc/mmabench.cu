@@ -73,3 +73,45 @@ extern "C" int metrpo_bench_mma(int ts_mode, int N, int reps, int two_acc, int a
   METRPO_CUDA_OK(cudaGetLastError());
   return METRPO_OK;
 }
+
+// Legacy warp-level tensor path (mma.sync) micro-benchmark: `warps` warps of one CTA each issue
+// reps x 8 independent MMAs (8 accumulator chains); kind 0: m16n8k8 tf32, 1: m16n8k16 bf16.
+// out_dev[0] = clock64 span of warp 0.  Priced here because the TRPO sample pass could use it.
+namespace metrpo {
+__global__ void mmasync_bench_kernel(int kind, int reps, unsigned long long* out) {
+  float c[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[i][q] = 0.f;
+  uint32_t a0 = threadIdx.x, a1 = threadIdx.x * 3, a2 = 7, a3 = 11, b0 = 5, b1 = 9;
+  __syncthreads();
+  const unsigned long long t0 = clock64();
+  for (int r = 0; r < reps; ++r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (kind == 0)
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+      else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+  }
+  const unsigned long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = static_cast<unsigned long long>(s != 12345.f); }
+}
+}  // namespace metrpo
+
+extern "C" int metrpo_bench_mma_sync(int kind, int warps, int reps, unsigned long long* out_dev, void* stream_) {
+  using namespace metrpo;
+  if (kind < 0 || kind > 1 || warps < 1 || warps > 32 || reps < 1) return set_error(METRPO_ERR_INVALID, "bench_mma_sync: bad argument");
+  mmasync_bench_kernel<<<1, warps * 32, 0, static_cast<cudaStream_t>(stream_)>>>(kind, reps, out_dev);
+  METRPO_CUDA_OK(cudaGetLastError());
+  return METRPO_OK;
+}

@@ -59,6 +59,13 @@ struct PassParams {
   const int* skip_flag;
 };
 
+// tanh(x) = 1 - 2/(exp(2x)+1) with ex2.approx / rcp.approx: abs error ~1e-7, ~6 instructions (the
+// same formula the rollout kernel uses for the policy it samples with, csrc/rollout_kernel.cuh)
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(2.f * x);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -89,7 +96,7 @@ __device__ __forceinline__ void layer_forward(const float* __restrict__ W, const
     }
 #pragma unroll
     for (int q = 0; q < 16; ++q)
-      if (j0 + q < nout) out[(j0 + q) * LD + n] = use_tanh ? tanhf(acc[q]) : acc[q];
+      if (j0 + q < nout) out[(j0 + q) * LD + n] = use_tanh ? tanh_fast(acc[q]) : acc[q];
   }
 }
 
@@ -351,6 +358,10 @@ __global__ void __launch_bounds__(NT) policy_pass_kernel(const __grid_constant__
   }
 }
 
+
+}  // namespace metrpo
+#include "trpo_mma.cuh"
+namespace metrpo {
 
 // ---------------------------------------------------------------------------------------------
 // CG / line-search controller: single-CTA kernels over P-vectors in double (rllab keeps the CG
@@ -741,6 +752,7 @@ struct metrpo_trpo {
   metrpo_allreduce_fn ar = nullptr;
   void* ar_user = nullptr;
   int last_launches = 0;
+  int pass_impl = METRPO_TRPO_PASS_AUTO;
 };
 
 static void trpo_free(metrpo_trpo* h) {
@@ -827,6 +839,14 @@ extern "C" int metrpo_trpo_destroy(metrpo_trpo_t* h) {
 
 extern "C" int metrpo_trpo_num_params(const metrpo_trpo_t* h) { return h ? h->pd.P : 0; }
 extern "C" int metrpo_trpo_last_launches(const metrpo_trpo_t* h) { return h ? h->last_launches : 0; }
+
+extern "C" int metrpo_trpo_set_pass_impl(metrpo_trpo_t* h, int impl) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "trpo_set_pass_impl: null handle");
+  if (impl < METRPO_TRPO_PASS_AUTO || impl > METRPO_TRPO_PASS_TF32X3)
+    return set_error(METRPO_ERR_INVALID, "trpo_set_pass_impl: unknown implementation %d", impl);
+  h->pass_impl = impl;
+  return METRPO_OK;
+}
 
 extern "C" int metrpo_trpo_set_allreduce(metrpo_trpo_t* h, metrpo_allreduce_fn fn, void* user) {
   if (!h) return set_error(METRPO_ERR_INVALID, "trpo_set_allreduce: null handle");
@@ -940,8 +960,28 @@ static int launch_pass_nt(metrpo_trpo* h, const PassParams& p, cudaStream_t st) 
   METRPO_CUDA_OK(cudaGetLastError());
   return METRPO_OK;
 }
+// tensor-core pass (trpo_mma.cuh): one persistent CTA of MMA_WARPS warps per SM
+template <int MODE, int NS>
+static int launch_pass_mma(metrpo_trpo* h, const PassParams& p, cudaStream_t st) {
+  const size_t smem = mma_smem_bytes(h->pd, MODE == MODE_FVP, NS == 3);
+  if (smem > static_cast<size_t>(h->max_smem)) return 1;
+  METRPO_CUDA_OK(cudaFuncSetAttribute(policy_pass_mma_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long tiles = (p.N + 31) / 32;
+  const int grid = static_cast<int>(std::min<long long>((tiles + MMA_WARPS - 1) / MMA_WARPS, h->num_sms));
+  policy_pass_mma_kernel<MODE, NS><<<grid, MMA_WARPS * 32, smem, st>>>(p);
+  METRPO_CUDA_OK(cudaGetLastError());
+  return METRPO_OK;
+}
 template <int MODE>
 static int launch_pass(metrpo_trpo* h, const PassParams& p, cudaStream_t st) {
+  if (h->pass_impl == METRPO_TRPO_PASS_TF32 || h->pass_impl == METRPO_TRPO_PASS_TF32X3) {
+    if (!mma_eligible(h->pd))
+      return set_error(METRPO_ERR_UNSUPPORTED, "trpo: the tensor-core pass covers <= 3 weight layers of width <= 32");
+    int rc = h->pass_impl == METRPO_TRPO_PASS_TF32 ? launch_pass_mma<MODE, 1>(h, p, st)
+                                                   : launch_pass_mma<MODE, 3>(h, p, st);
+    if (rc == METRPO_OK) { ++h->last_launches; return rc; }
+    if (rc != 1) return rc;
+  }
   int rc = launch_pass_nt<MODE, 128>(h, p, st);
   if (rc == 1) rc = launch_pass_nt<MODE, 64>(h, p, st);
   if (rc == 1) rc = launch_pass_nt<MODE, 32>(h, p, st);

@@ -77,11 +77,13 @@ _PROTOS = {
     "metrpo_rollout_get_trace": (_i, [_vp, _vp]),
     "metrpo_debug_schedule": (_i, [_i, _i, _i, _vp, _i]),
     "metrpo_bench_mma": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "metrpo_bench_mma_sync": (_i, [_i, _i, _i, _vp, _vp]),
     "metrpo_selftest_umma": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "metrpo_trpo_create": (_i, [ctypes.POINTER(TrpoCfg), ctypes.POINTER(_vp)]),
     "metrpo_trpo_destroy": (_i, [_vp]),
     "metrpo_trpo_set_allreduce": (_i, [_vp, ALLREDUCE_FN, _vp]),
     "metrpo_trpo_num_params": (_i, [_vp]),
+    "metrpo_trpo_set_pass_impl": (_i, [_vp, _i]),
     "metrpo_trpo_last_launches": (_i, [_vp]),
     "metrpo_trpo_process": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "metrpo_trpo_fit_baseline": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp]),

@@ -46,6 +46,12 @@ class PolicyUpdate:
         except Exception:
             pass
 
+    def set_pass_impl(self, impl):
+        """'auto' (fastest measured: SIMT today), 'simt' (fp32 CUDA cores), 'tf32' / 'tf32x3'
+        (warp-level tensor-core MMAs, single / split products)."""
+        _lib.check(self._lib.metrpo_trpo_set_pass_impl(self._h, {"auto": 0, "simt": 1, "tf32": 2, "tf32x3": 3}[impl]),
+                   "trpo_set_pass_impl")
+
     # -- multi-GPU: sum the (tiny) accumulators across ranks with torch.distributed -------------
     def enable_allreduce(self, group=None):
         """Registers an all-reduce callback: every reduction of the update (gradient, each

@@ -82,6 +82,41 @@ def test_gradient_fvp_loss_match_autograd(env, N, hidden, out_tanh):
     pu.close()
 
 
+@pytest.mark.parametrize("impl,tol_l,tol_g", [("tf32x3", 2e-5, 2e-4), ("tf32", 2e-3, 5e-3)])
+@pytest.mark.parametrize("env,N,out_tanh", [("half-cheetah", 1000, False), ("ant", 517, True), ("hopper", 95, False)])
+def test_tensor_core_pass_variants_match_oracle(env, N, out_tanh, impl, tol_l, tol_g):
+    """The warp-level tensor-core implementations of the sample pass (metrpo_trpo_set_pass_impl;
+    not the default, see csrc/trpo_mma.cuh) against the float64 autograd oracle: the 3xTF32 split
+    to the same tolerance as the fp32 SIMT pass, plain TF32 to 10-bit-mantissa tolerances."""
+    from oracle import trpo as ot
+    from me_trpo_b200.trpo import PolicyUpdate
+    pr = _problem(env, N, hidden=(32, 32), out_tanh=out_tanh)
+    orc = ot.TRPOOracle(pr["dims"], out_tanh=out_tanh)
+    theta = ot.flatten_params(pr["pol"])
+    rng = np.random.RandomState(1)
+    theta_new = theta + rng.normal(0, 0.02, theta.shape)
+    pu = PolicyUpdate(pr["dims"], out_tanh=out_tanh, device="cuda:0")
+    pu.set_pass_impl(impl)
+    d = _dev(pr)
+    th_d = torch.tensor(theta_new.astype(np.float32), device="cuda")
+    l_dev, k_dev = pu.loss_kl(th_d, **d)
+    l_ref, k_ref = orc.loss_kl(theta_new.astype(np.float32), _oracle_inputs(pr))
+    assert abs(l_dev - l_ref) <= tol_l and abs(k_dev - k_ref) <= tol_l
+    assert _rel(pu.grad(th_d, **d), orc.grad(theta_new.astype(np.float32), _oracle_inputs(pr))) <= tol_g
+    th0_d = torch.tensor(theta.astype(np.float32), device="cuda")
+    v = rng.normal(size=theta.shape).astype(np.float32)
+    hv_dev = pu.grad(th0_d, **d, vec=torch.tensor(v, device="cuda"), reg_coeff=1e-5)
+    assert _rel(hv_dev, orc.hvp(theta.astype(np.float32), _oracle_inputs(pr), v)) <= tol_g
+    pu.close()
+    # wide policies are refused by this implementation, not silently routed elsewhere
+    pw = PolicyUpdate([55, 100, 50, 25, 21], device="cuda:0")
+    pw.set_pass_impl(impl)
+    with pytest.raises(RuntimeError):
+        pw.loss_kl(torch.zeros(pw.P, device="cuda"), torch.zeros(4, 55, device="cuda"), torch.zeros(4, 21, device="cuda"),
+                   torch.zeros(4, device="cuda"), torch.zeros(4, 21, device="cuda"), torch.zeros(21, device="cuda"))
+    pw.close()
+
+
 def test_valid_mask_and_per_sample_log_std():
     from oracle import trpo as ot
     from me_trpo_b200.trpo import PolicyUpdate

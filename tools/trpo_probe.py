@@ -16,6 +16,8 @@ ro = EnsembleRollout("half-cheetah", K, B, T, hidden=1024, device="cuda:0")
 ro.set_dynamics_ensemble(models); ro.set_normalization(**norm); ro.set_policy(pol["W"], pol["b"], pol["log_std"])
 out = ro.run(T, init, pool, seed=3); ro.synchronize()
 pu = PolicyUpdate([spec["S"], 32, 32, spec["A"]], device="cuda:0")
+IMPL = sys.argv[2] if len(sys.argv) > 2 else "auto"
+pu.set_pass_impl(IMPL)
 parts = []
 for W, b in zip(pol["W"], pol["b"]):
     parts += [W.ravel(), b.ravel()]
@@ -45,9 +47,9 @@ t_fvp, _ = timed(lambda: pu.grad(th, out["obs"], out["act"], pr2["adv"], out["me
 t_loss, _ = timed(lambda: pu.loss_kl(th, out["obs"], out["act"], pr2["adv"], out["mean"], ls, valid=pr2["valid"]))
 N = T * B
 bytes_pass = N * 4 * (spec["S"] + 2 * spec["A"] + 1) + N
-res = dict(T=T, B=B, N=N, ms_process=t_proc, ms_process_with_baseline=t_proc2, ms_fit_baseline=t_fit,
+res = dict(impl=IMPL, T=T, B=B, N=N, ms_process=t_proc, ms_process_with_baseline=t_proc2, ms_fit_baseline=t_fit,
            ms_update=t_upd, ms_grad=t_grad, ms_fvp=t_fvp, ms_loss=t_loss,
            pass_GBps=dict(grad=bytes_pass / t_grad / 1e6, fvp=bytes_pass / t_fvp / 1e6, loss=bytes_pass / t_loss / 1e6),
            info=info.cpu().tolist(), launches=pu.last_launches())
 print(json.dumps(res))
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "trpo_probe.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "trpo_probe_%s.json" % IMPL), "w"), indent=1)
