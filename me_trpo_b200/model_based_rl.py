@@ -169,3 +169,139 @@ def optimize_policy(algo, policy_opt_params, policy_validation_init, logger=None
             "best_cost": min_val_cost, "trpo_mean_costs": trpo_mean_costs,
             "real_current_validation_cost": real_current_validation_cost,
             "min_validation_costs": min_validation_costs}
+
+
+# ================================================================================================
+# Outer loop: collect -> fit the ensemble -> improve the policy  (model_based_rl.py:231-755)
+# ================================================================================================
+def sample_trajectories(real_env, policy, exploration, batch_size, max_timestep, rng, logger=None):
+    """env_helpers.py:352-460 without parameter-space noise (prepare_policy perturbs TF variables
+    between episodes; exploration here is the action noise only -- real-environment collection is
+    outside the hot path).  Returns (Os, As, Rs, info)."""
+    import torch
+    Os, As, Rs = [], [], []
+    counter = 1
+    with torch.no_grad():
+        W = [w.cpu().numpy().astype(np.float64) for w in policy.W]
+        b = [v.cpu().numpy().astype(np.float64) for v in policy.b]
+    n = len(W)
+
+    def mean_action(o):
+        h = o
+        for i in range(n):
+            h = h @ W[i] + b[i]
+            if i < n - 1 or policy.output_tanh:
+                h = np.tanh(h)
+        return h
+
+    while counter <= batch_size:
+        o, a, r = [real_env.reset()], [], []
+        for t in range(max_timestep):
+            noise = exploration["action_noise"] * (rng.uniform() if exploration.get("vary_trajectory_noise") else 1.0)
+            act = np.clip(mean_action(o[-1]) + noise * rng.normal(size=real_env.A), -1.0, 1.0)   # get_action
+            obs, rew, done, _ = real_env.step(act)
+            o.append(obs); a.append(act); r.append(rew)
+            counter += 1
+            if done:
+                break
+        Os.append(o); As.append(a); Rs.append(r)
+    info = dict(EpisodesCollected=len(Os), TimeStepsCollected=counter - 1,
+                avg_eps_reward=float(np.mean([np.sum(x) for x in Rs])))
+    return Os, As, Rs, info
+
+
+def collect_data(real_env, policy, sample_size, dynamics_data, dynamics_validation, input_rms, output_rms,
+                 rollout_params, rng, logger=None):
+    """model_based_rl.py:758-857 (use_same_dataset / trajectory split)."""
+    from .dynamics import add_rollout_data
+    if sample_size == 0:
+        return {}
+    Os, As, Rs, info = sample_trajectories(real_env, policy, rollout_params["exploration"], sample_size,
+                                           rollout_params["max_timestep"], rng, logger)
+    x_all, y_all = [], []
+    for o, a in zip(Os, As):
+        for t in range(len(o) - 1):
+            x_all.append(np.concatenate([o[t], a[t]]))
+            y_all.append(o[t + 1])
+    x_all, y_all = np.asarray(x_all, np.float32), np.asarray(y_all, np.float32)
+    assert len(x_all) >= sample_size
+    add_rollout_data(x_all, y_all, dynamics_data, dynamics_validation, input_rms, output_rms,
+                     rollout_params["split_ratio"])
+    return info
+
+
+def train_models(real_env, nn_env, algo, fit, params, snapshot_dir=None, seed=0, logger=None,
+                 sweep_iters=None, policy_validation_init=None):
+    """The sweep loop of train_models (model_based_rl.py:546-755) for algo 'trpo': every sweep
+    collects `sample_size` real transitions, refits the K dynamics models on the device
+    (optimize_models), pushes the new weights + normalisers into the imaginary env, resets
+    log_std (training.py:368-370) and runs optimize_policy.  One progress.csv row per sweep with
+    the reference's column names."""
+    import csv
+    import os
+    import time
+    import torch
+    from .dynamics import RunningMeanStd, data_collection, optimize_models
+    logger = logger or logging.getLogger("me_trpo_b200")
+    rng = np.random.RandomState(seed)
+    rp, dop, pop_json = params["rollout_params"], params["dynamics_opt_params"], params["policy_opt_params"]
+    pop = policy_opt_params_from_json(pop_json)
+    policy = algo.policy
+    dev = fit.device
+    dynamics_data = data_collection(rp["training_data_size"], dev)
+    dynamics_validation = data_collection(rp["validation_data_size"], dev)
+    input_rms = RunningMeanStd(shape=(fit.S + fit.A,), device=dev)
+    diff_rms = RunningMeanStd(shape=(fit.S,), device=dev)
+    if policy_validation_init is None:                                      # :444-487
+        policy_validation_init = np.asarray([real_env.reset() for _ in range(pop.batch_size)], np.float32)
+    sweep_iters = int(sweep_iters or params["sweep_iters"])
+    rows, start_time = [], time.time()
+    diff_weights = None
+    for count in range(1, sweep_iters + 1):
+        t0 = time.time()
+        reinit_every = int(dop["reinitialize"])
+        reinitialize = (count == 1) or not (reinit_every <= 0 or count % reinit_every != 1)   # :550-556
+        info = collect_data(real_env, policy, params["sample_size"], dynamics_data, dynamics_validation,
+                            input_rms, diff_rms, rp, rng, logger)
+        t1 = time.time()
+        norm = dict(in_mean=input_rms.mean, in_std=input_rms.std, diff_mean=diff_rms.mean, diff_std=diff_rms.std)
+        fit.set_normalization(**norm)
+        dlog = optimize_models(fit, dynamics_data, dynamics_validation, batch_size=min(dop["batch_size"], fit.max_rows),
+                               learning_rate=dop["learning_rate"], log_every=dop["log_every"],
+                               num_passes_threshold=dop["num_passes_threshold"], max_passes=dop["max_passes"],
+                               reinitialize=reinitialize, rng=None, seed=seed + count, logger=None)
+        torch.cuda.synchronize()
+        t2 = time.time()
+        nn_env.models = fit.get_ensemble()                                   # new weights -> imaginary env
+        nn_env.norm = {k: v.clone() for k, v in norm.items()}
+        if pop_json["trpo"].get("reset", False):                             # training.py:368-370
+            policy.log_std.fill_(float(np.log(pop_json["trpo"]["init_std"])))
+        old_w = policy.get_param_values()
+        plog = optimize_policy(algo, pop, policy_validation_init, logger=logger)
+        new_w = policy.get_param_values()
+        torch.cuda.synchronize()
+        t3 = time.time()
+        if (np.abs(new_w - old_w) > 0).any():
+            diff_weights = np.abs(new_w - old_w)
+        row = {"collect_data_time": t1 - t0, "model_opt_time": t2 - t1, "policy_opt_time": t3 - t2,
+               "Time": time.time() - start_time, "ItrTime": time.time() - t0,
+               "MaxPolicyWeightDiff": float(np.amax(diff_weights)) if diff_weights is not None else 0,
+               "MinPolicyWeightDiff": float(np.amin(diff_weights)) if diff_weights is not None else 0,
+               "AvgPolicyWeightDiff": float(np.mean(diff_weights)) if diff_weights is not None else 0,
+               "EpisodesCollected": info.get("EpisodesCollected", 0),
+               "TimeStepsCollected": info.get("TimeStepsCollected", 0),
+               "# model updates": dlog["n_updates"],
+               "training_dynamics_min_sum_validation_loss": dlog["min_sum_validation_loss"],
+               "estimated_policy_mean_min_validation_cost": float(np.mean(plog["min_validation_costs"]["estimated"])),
+               "real_policy_mean_min_validation_cost": float(np.mean(plog["min_validation_costs"]["real"])),
+               "real_current_validation_cost": plog["real_current_validation_cost"],
+               "# policy updates": plog["best_index"], "avg_eps_reward": info.get("avg_eps_reward", 0.0)}
+        rows.append(row)
+        logger.info("sweep %d: %s" % (count, {k: (round(v, 4) if isinstance(v, float) else v) for k, v in row.items()}))
+        if snapshot_dir:
+            os.makedirs(snapshot_dir, exist_ok=True)
+            with open(os.path.join(snapshot_dir, "progress.csv"), "w", newline="") as f:
+                w = csv.DictWriter(f, fieldnames=list(rows[0].keys()))
+                w.writeheader()
+                w.writerows(rows)
+    return rows
