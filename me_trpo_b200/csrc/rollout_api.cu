@@ -1,5 +1,6 @@
 // C-ABI entry points of the ensemble-rollout path (include/metrpo.h): handle management, weight
 // packing into the bf16 tile stream, gang schedule construction and kernel launch.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -108,6 +109,8 @@ struct metrpo_rollout {
   int smax, amax;
   uint32_t tm_acc0, tm_acc2, tm_h0, tm_z;
   int pol_in_smem;
+  int rec_stride = 0;
+  size_t xbuf_slot_floats = 0;
   uint32_t stage_bytes, w0g_bytes, w2chunk_bytes, off_w2, off_w0g;
   size_t model_stride;
   // device buffers
@@ -137,6 +140,7 @@ struct metrpo_rollout {
   std::vector<char> dyn_set;
   bool norm_set = false, pol_set = false, state_set = false;
   int last_launches = 0;
+  bool disable_own = false;   // dev / test switch: force the all-candidates exchange
 };
 
 static uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -221,6 +225,10 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   h->off_w0g = h->off_w2 + h->NC * h->w2chunk_bytes;
   h->model_stride = align_up(h->off_w0g + (c.hidden / 128) * h->w0g_bytes, 1024);
   h->dyn_set.assign(c.n_models, 0);
+  {
+    const char* ev = getenv("METRPO_DISABLE_OWN");   // dev switch: A/B the two exchange protocols
+    h->disable_own = ev && ev[0] == '1';
+  }
 
   // policy blob layout
   int off = 0;
@@ -237,7 +245,7 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   // activation rows of the policy in the scratch area: region A holds the layer-0 input (x) and
   // doubles as the Z staging area [S+A rows]; a hidden layer of <= 32 outputs writes in place,
   // a wider one writes to the other region
-  int region_rows[2] = {c.state_dim + c.action_dim, 0};
+  int region_rows[2] = {c.state_dim + c.action_dim + 1, 0};   // +1: odd row stride of the own_mode policy inputs
   {
     int cur = 0;
     for (int l = 0; l < c.n_policy_layers; ++l) {
@@ -289,7 +297,9 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   alloc(reinterpret_cast<void**>(&h->bias), static_cast<size_t>(c.n_models) * (2 * c.hidden + BIAS_PAD) * 4);
   alloc(reinterpret_cast<void**>(&h->norm), (2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4);
   alloc(reinterpret_cast<void**>(&h->pol), h->pol_floats * 4);
-  alloc(reinterpret_cast<void**>(&h->xbuf), static_cast<size_t>(h->max_slots) * 2 * c.n_models * c.state_dim * TILE_M * 4);
+  h->rec_stride = 8 + 4 + static_cast<int>(align_up(c.state_dim, 4));   // [a_raw 8 | done, pad | x_new] (narrow instantiation)
+  h->xbuf_slot_floats = static_cast<size_t>(std::max(c.n_models * c.state_dim, h->rec_stride)) * TILE_M;
+  alloc(reinterpret_cast<void**>(&h->xbuf), static_cast<size_t>(h->max_slots) * 2 * h->xbuf_slot_floats * 4);
   alloc(reinterpret_cast<void**>(&h->xctr), h->max_slots * 4);
   alloc(reinterpret_cast<void**>(&h->row_state), rows_pad * c.state_dim * 4);
   alloc(reinterpret_cast<void**>(&h->row_ts), rows_pad * 4);
@@ -489,6 +499,12 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
   p.NC = h->NC; p.KC = h->KC; p.N1 = h->N1; p.row_offset = c.row_offset;
   p.tm_acc0 = h->tm_acc0; p.tm_acc2 = h->tm_acc2; p.tm_h0 = h->tm_h0; p.tm_z = h->tm_z;
   p.pol_in_smem = h->pol_in_smem;
+  // row-ownership exchange: selection modes only (every row has exactly one source model per step)
+  p.own_mode = (!h->big && c.n_models > 1 && !p.per_model && p.ext_actions == nullptr &&
+                (c.sam_mode == METRPO_SAM_STEP_RAND || c.sam_mode == METRPO_SAM_EPS_RAND) && !h->disable_own) ? 1 : 0;
+  p.rec_stride = h->rec_stride;
+  p.xbuf_stride = h->xbuf_slot_floats;
+  p.slot_stride = (c.state_dim + c.action_dim) | 1;
   p.n_tiles = p.per_model ? (p.B + TILE_M - 1) / TILE_M : h->n_tiles;
   p.wstream = h->wstream; p.model_stride = h->model_stride; p.stage_bytes = h->stage_bytes;
   p.w0g_bytes = h->w0g_bytes; p.w2chunk_bytes = h->w2chunk_bytes; p.off_w2 = h->off_w2;

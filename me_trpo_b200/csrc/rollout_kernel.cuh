@@ -102,6 +102,11 @@ struct KParams {
   int NC, KC, N1;        // layer-1 passes, 64-wide reduction chunks, pass width (256 or 128)
   uint32_t tm_acc0, tm_acc2, tm_h0, tm_z;   // TMEM column offsets
   int pol_in_smem;       // policy blob staged in shared memory (else read through L1 from global)
+  int own_mode;          // 1: row-ownership exchange (step_rand / eps_rand, K > 1): the CTA whose model a
+                         //    row selects this step computes reward / done / reset / next action for it
+  int rec_stride;        // own_mode: floats per row record in xbuf  [a_raw AMAX | done, pad 3 | x_new S, pad to 4]
+  int slot_stride;       // own_mode: floats per compacted policy input row in the scratch area
+  unsigned long long xbuf_stride;   // floats per (slot, parity) exchange buffer
   int n_steps, n_slots, n_tiles;
   int resume;            // 1: state comes from row_state (B1 step / continued run)
   int per_model;         // 1: per-model validation-cost rollout (model_based_rl.py:122-142): every
@@ -364,6 +369,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint32_t tmem_slot;
   __shared__ int abort_smem;
+  // row-ownership mode (narrow instantiation only): compacted row list, per-row policy noise of
+  // the next step, hidden activations of one policy pass (32 rows x 4 threads)
+  constexpr int OWN_ON = (SMAX <= 32) ? 1 : 0;
+  __shared__ int sList[OWN_ON ? TILE_M : 1];
+  __shared__ int sCnt[4];
+  __shared__ __align__(16) float sEpsRow[OWN_ON ? TILE_M * AMAX : 4];
+  __shared__ float sHid[OWN_ON ? 2 * 64 * 33 : 1];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slot = blockIdx.x / p.K, k = blockIdx.x % p.K;
@@ -680,6 +692,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
       int est = 0;   // steps done by this CTA (trace window index, same as the MMA warp's st)
       float ep[AMAX];          // N(0,1) policy noise of the upcoming step
       bool ep_valid = false;
+      bool have_action = false;   // own_mode: a_raw of the upcoming step came with the exchange record
+      int own_idx = 0;            // own_mode: model this thread's row selects in the current step
       int row = 0;
       bool valid = false;
       float pm_acc = 0.f, pm_gpow = 1.f, pm_dmask = 0.f;   // per_model: cost sum, gamma^t, Ant dones
@@ -711,6 +725,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
         row = tile * TILE_M + r;
         valid = row < p.B;
         ep_valid = false;
+        have_action = false;
 
         // ---- segment start: acquire the tile's state ----
         if (sg.w) {
@@ -742,6 +757,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               a_raw[i] = (valid && i < A) ? p.ext_actions[row * A + i] : 0.f;
               a_mean[i] = a_raw[i];
             }
+          } else if (have_action) {
+            // own_mode: the action of this step was computed by the row's owner at the end of the
+            // previous step and arrived with the exchange record (a_raw; act / mean already stored)
           } else {
             // policy mean network (training.py:99-103), fp32 on CUDA cores.  Activations live in
             // the thread's own column of the scratch rows.
@@ -805,6 +823,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                 a_raw[i] = (i < A) ? __fadd_rn(__fmul_rn(ep[i], expf(ls)), a_mean[i]) : 0.f;
               }
             }
+            if (p.own_mode && k == 0 && valid) {   // first step of a segment: nobody stored these yet
+              const size_t o = static_cast<size_t>(t) * p.B + row;
+#pragma unroll
+              for (int i = 0; i < AMAX; ++i)
+                if (i < A) {
+                  if (p.act) p.act[o * A + i] = a_raw[i];
+                  if (p.mean) p.mean[o * A + i] = a_mean[i];
+                }
+            }
           }
           TRACE(2, 0x1011);
           // z = (concat(x, clip(a)) - in_mean) * (1 / in_std), drop leading cols  (training.py:228,146-154)
@@ -834,6 +861,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           tc_fence_before();
           mbar_arrive(&bars[B_ZREADY]);
           TRACE(2, 0x1001);
+          if constexpr (SMAX <= 32) {
+            // own_mode: policy noise of step t+1 for this thread's row, parked in shared memory
+            // (same thread reads it back at the end of the step if it owns the row)
+            if (p.own_mode) {
+              if (!p.determ && t + 1 < t1) {
+                load_eps(t + 1);
+                ep_valid = false;
+#pragma unroll
+                for (int i = 0; i < AMAX; i += 4)
+                  *reinterpret_cast<float4*>(&sEpsRow[r * AMAX + i]) = make_float4(ep[i], ep[i + 1], ep[i + 2], ep[i + 3]);
+              }
+              // model index of this step, off the critical path (ts / nreset are final here)
+              if (p.model_idx != nullptr)
+                own_idx = valid ? p.model_idx[static_cast<size_t>(t) * p.B + row] : 0;
+              else if (p.sam_mode == METRPO_SAM_STEP_RAND)
+                own_idx = philox_index(p.seed, static_cast<uint32_t>(p.offset + t),
+                                       static_cast<uint32_t>(row + p.row_offset), PHILOX_STREAM_IDX, K);
+              else
+                own_idx = philox_index(p.seed, static_cast<uint32_t>(nreset),
+                                       static_cast<uint32_t>(row + p.row_offset), PHILOX_STREAM_EIDX, K);
+              own_idx = min(max(own_idx, 0), K - 1);
+            }
+          }
 
           // ================= per-group epilogues (2 chunks of 64 hidden columns) =================
           {
@@ -948,13 +998,205 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               }
             }
           }
+          bool handled = false;
+          if constexpr (SMAX <= 32) {
+            if (p.own_mode) {
+              // ============ row-ownership exchange (step_rand / eps_rand) ============
+              // Every CTA of the gang knows which model each row selects this step.  The CTA of
+              // that model already holds the row's next state (its own candidate), so it alone
+              // computes reward / done / reset and the NEXT step's action for the row -- with four
+              // threads per owned row (~128/K rows) instead of every CTA redundantly running the
+              // policy for all 128 rows -- and publishes one record [x_new | a_raw | done] per row.
+              handled = true;
+              const int RS = p.rec_stride, SPs = p.slot_stride;
+              float* rec = p.xbuf + static_cast<size_t>(slot * 2 + (xn_cnt & 1)) * p.xbuf_stride;
+              const bool own = valid && own_idx == k;
+              const bool want_pol = (t + 1 < t1);
+              TRACE(2, 0x1020);
+              if (own) {
+                float u[AMAX];
+#pragma unroll
+                for (int i = 0; i < AMAX; ++i) u[i] = fminf(fmaxf(a_raw[i], -1.f), 1.f);
+                const float reward = -env_cost<SMAX, AMAX>(p.env_id, S, A, cand, u);   // env_helpers.py:601
+                const bool dn = env_is_done<SMAX>(p.env_id, S, cand) || (ts + 1 >= p.T_max);   // :603-604
+                const size_t o = static_cast<size_t>(t) * p.B + row;
+                if (p.obs) {
+#pragma unroll
+                  for (int s = 0; s < SMAX; ++s)
+                    if (s < S) p.obs[o * S + s] = x[s];
+                }
+                if (p.rew) p.rew[o] = reward;
+                if (p.done) p.done[o] = dn ? 1 : 0;
+                if (dn) {   // :605-606 -> reset(dones)
+                  const float* src = p.reset_pool + static_cast<size_t>((static_cast<long long>(nreset) * p.B + row) % p.R) * S;
+#pragma unroll
+                  for (int s = 0; s < SMAX; ++s)
+                    if (s < S) cand[s] = src[s];
+                }
+                float4* rq = reinterpret_cast<float4*>(rec + r * RS);
+                rq[AMAX / 4] = make_float4(dn ? 1.f : 0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < SMAX / 4; ++q)
+                  if (4 * q < S) rq[AMAX / 4 + 1 + q] = make_float4(cand[4 * q], cand[4 * q + 1], cand[4 * q + 2], cand[4 * q + 3]);
+              }
+              // ---- compact the owned rows of the tile ----
+              const unsigned om = __ballot_sync(0xffffffffu, own);
+              if (lane == 0) sCnt[warp & 3] = __popc(om);
+              named_bar_sync(1, EPI_THREADS);
+              int off = 0, n_own = 0;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                const int c = sCnt[w];
+                if (w < (warp & 3)) off += c;
+                n_own += c;
+              }
+              if (own) {
+                const int j = off + __popc(om & ((1u << lane) - 1u));
+                sList[j] = r;
+                float* in = scrA + j * SPs;
+#pragma unroll
+                for (int s = 0; s < SMAX; ++s)
+                  if (s < S) in[s] = cand[s];
+                if (want_pol && !p.determ) {
+#pragma unroll
+                  for (int i = 0; i < AMAX; ++i)
+                    if (i < A) in[S + i] = sEpsRow[r * AMAX + i];
+                }
+              }
+              named_bar_sync(1, EPI_THREADS);
+              TRACE(2, 0x1021);
+              // ---- policy of step t+1 for the owned rows: 2 threads per row, 64 rows per pass (one
+              //      pass unless a CTA owns more than half of the tile) ----
+              if (want_pol) {
+                const int part = e & 1, jl = e >> 1;
+                const int nl = p.n_pol_layers;
+                for (int base = 0; base < n_own; base += 64) {
+                  const int j = base + jl;
+                  const bool actv = j < n_own;
+                  const float* cur = scrA + (actv ? j : 0) * SPs;
+                  for (int l = 0; l < nl - 1; ++l) {
+                    const PolicyLayer& L = p.pl[l];
+                    float acc[16];
+                    {
+                      const float4* b4 = reinterpret_cast<const float4*>(sPolS + L.b_off + 16 * part);
+#pragma unroll
+                      for (int q = 0; q < 4; ++q) {
+                        const float4 b = b4[q];
+                        acc[4 * q] = b.x; acc[4 * q + 1] = b.y; acc[4 * q + 2] = b.z; acc[4 * q + 3] = b.w;
+                      }
+                    }
+                    const float* W = sPolS + L.w_off + 16 * part;
+#pragma unroll 2
+                    for (int i = 0; i < L.nin; ++i) {
+                      const float xi = cur[i];
+                      const float4* w4 = reinterpret_cast<const float4*>(W + i * HPB);
+#pragma unroll
+                      for (int q = 0; q < 4; ++q) {
+                        const float4 w = w4[q];
+                        acc[4 * q] = __fmaf_rn(xi, w.x, acc[4 * q]); acc[4 * q + 1] = __fmaf_rn(xi, w.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = __fmaf_rn(xi, w.z, acc[4 * q + 2]); acc[4 * q + 3] = __fmaf_rn(xi, w.w, acc[4 * q + 3]);
+                      }
+                    }
+                    float* out = sHid + (l & 1) * (64 * 33) + jl * 33 + 16 * part;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) out[c] = fast_tanh(acc[c]);
+                    __syncwarp();
+                    cur = sHid + (l & 1) * (64 * 33) + jl * 33;
+                  }
+                  const PolicyLayer& L = p.pl[nl - 1];
+                  float mo[AMAX / 2];
+#pragma unroll
+                  for (int c = 0; c < AMAX / 2; ++c) mo[c] = sPolS[L.b_off + (AMAX / 2) * part + c];
+                  {
+                    const float* W = sPolS + L.w_off + (AMAX / 2) * part;
+#pragma unroll 4
+                    for (int i = 0; i < L.nin; ++i) {
+                      const float xi = cur[i];
+                      const float4 w = *reinterpret_cast<const float4*>(W + i * AMAX);
+                      mo[0] = __fmaf_rn(xi, w.x, mo[0]); mo[1] = __fmaf_rn(xi, w.y, mo[1]);
+                      mo[2] = __fmaf_rn(xi, w.z, mo[2]); mo[3] = __fmaf_rn(xi, w.w, mo[3]);
+                    }
+                  }
+                  if (p.pol_out_tanh) {
+#pragma unroll
+                    for (int c = 0; c < AMAX / 2; ++c) mo[c] = tanhf(mo[c]);
+                  }
+                  if (actv) {
+                    const int rowl = sList[j];
+                    const float* in = scrA + j * SPs;
+                    const size_t o = static_cast<size_t>(t + 1) * p.B + (tile * TILE_M + rowl);
+#pragma unroll
+                    for (int q = 0; q < AMAX / 2; ++q) {
+                      const int c = (AMAX / 2) * part + q;
+                      if (c < A) {
+                        const float mu = mo[q];
+                        float raw = mu;
+                        if (!p.determ) {   // a = eps * exp(log_std) + mean   (rllab get_actions)
+                          const float ls = fmaxf(sPolS[p.pol_logstd_off + c], -13.815510557964274f);
+                          raw = __fadd_rn(__fmul_rn(in[S + c], expf(ls)), mu);
+                        }
+                        if (p.act) p.act[o * A + c] = raw;
+                        if (p.mean) p.mean[o * A + c] = mu;
+                        rec[rowl * RS + c] = raw;
+                      }
+                    }
+                  }
+                  __syncwarp();
+                }
+              }
+              TRACE(2, 0x1022);
+              // ---- publish / meet the gang: one release + one acquire poll per warp ----
+              __syncwarp();
+              int okw = 1;
+              if (lane == 0) {
+                red_release_gpu_add(&p.xctr[slot], 1u);
+                okw = wait_ge(&p.xctr[slot], 4u * static_cast<unsigned>(K) * (xn_cnt + 1), p.dbg, 101u,
+                              (uint32_t)st_dbg) ? 1 : 0;
+              }
+              okw = __shfl_sync(0xffffffffu, okw, 0);
+              if (!okw) goto bail;
+              TRACE(2, 0x1023);
+              ++xn_cnt;
+              float dnf = 0.f;
+              if (valid) {
+                const float4* rq = reinterpret_cast<const float4*>(rec + r * RS);
+                float4 qa[AMAX / 4], qx[SMAX / 4];
+#pragma unroll
+                for (int q = 0; q < AMAX / 4; ++q) qa[q] = want_pol ? __ldcg(rq + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 qd = __ldcg(rq + AMAX / 4);
+#pragma unroll
+                for (int q = 0; q < SMAX / 4; ++q)
+                  if (4 * q < S) qx[q] = __ldcg(rq + AMAX / 4 + 1 + q);
+#pragma unroll
+                for (int q = 0; q < AMAX / 4; ++q) {
+                  a_raw[4 * q] = qa[q].x; a_raw[4 * q + 1] = qa[q].y; a_raw[4 * q + 2] = qa[q].z; a_raw[4 * q + 3] = qa[q].w;
+                }
+#pragma unroll
+                for (int i = 0; i < AMAX; ++i)
+                  if (i >= A) a_raw[i] = 0.f;
+#pragma unroll
+                for (int q = 0; q < SMAX / 4; ++q)
+                  if (4 * q < S) {
+                    x[4 * q] = qx[q].x; x[4 * q + 1] = qx[q].y; x[4 * q + 2] = qx[q].z; x[4 * q + 3] = qx[q].w;
+                  }
+#pragma unroll
+                for (int s = 0; s < SMAX; ++s)
+                  if (s >= S) x[s] = 0.f;
+                dnf = qd.x;
+              }
+              if (dnf != 0.f) { ts = 0; nreset += 1; } else { ts += 1; }
+              have_action = want_pol;
+              TRACE(2, 0x1005);
+            }
+          }
+          if (!handled) {
           float xnext[SMAX];
           const int mode = p.sam_mode;
           if (K == 1 || p.per_model) {
 #pragma unroll
             for (int s = 0; s < SMAX; ++s) xnext[s] = cand[s];
           } else {
-            float* xb = p.xbuf + static_cast<size_t>((slot * 2 + (xn_cnt & 1)) * K) * S * TILE_M;
+            float* xb = p.xbuf + static_cast<size_t>(slot * 2 + (xn_cnt & 1)) * p.xbuf_stride;
 #pragma unroll
             for (int s = 0; s < SMAX; ++s)
               if (s < S) xb[(k * S + s) * TILE_M + r] = cand[s];
@@ -1109,6 +1351,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
             nreset += 1;
             ts = 0;
           }
+          }  // !handled
         }  // t
 
         // ---- segment end: publish the tile's state ----
