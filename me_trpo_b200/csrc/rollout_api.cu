@@ -271,7 +271,15 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   h->off_stage = o; o += NSTAGE * h->stage_bytes;
   h->off_sw0g = o; o += 2 * h->w0g_bytes;
   o = align_up(o, 1024); h->off_sw2 = o; o += h->w2chunk_bytes;
-  h->off_scr = o; o += (region_rows[0] + region_rows[1]) * TILE_M * 4;
+  {
+    int scr_floats = (region_rows[0] + region_rows[1]) * TILE_M;
+    if (h->big) {   // own_mode buffers of the wide instantiation live in the scratch area
+      const int slot_stride = (c.state_dim + c.action_dim) | 1;
+      const int need = ((TILE_M * slot_stride + 3) & ~3) + TILE_M * h->amax + 2 * (TILE_M / 16) * (HPMAX + 1);
+      scr_floats = std::max(scr_floats, need);
+    }
+    h->off_scr = o; o += align_up(scr_floats * 4, 16);
+  }
   h->off_sbias = o; o += (2 * c.hidden + BIAS_PAD) * 4;
   h->off_snorm = o; o += align_up((2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4, 16);
   h->off_spol = o; o += h->pol_in_smem ? align_up(h->pol_floats * 4, 16) : 0;
@@ -297,7 +305,7 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   alloc(reinterpret_cast<void**>(&h->bias), static_cast<size_t>(c.n_models) * (2 * c.hidden + BIAS_PAD) * 4);
   alloc(reinterpret_cast<void**>(&h->norm), (2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4);
   alloc(reinterpret_cast<void**>(&h->pol), h->pol_floats * 4);
-  h->rec_stride = 8 + 4 + static_cast<int>(align_up(c.state_dim, 4));   // [a_raw 8 | done, pad | x_new] (narrow instantiation)
+  h->rec_stride = h->amax + 4 + static_cast<int>(align_up(c.state_dim, 4));   // [a_raw AMAX | done, pad | x_new]
   h->xbuf_slot_floats = static_cast<size_t>(std::max(c.n_models * c.state_dim, h->rec_stride)) * TILE_M;
   alloc(reinterpret_cast<void**>(&h->xbuf), static_cast<size_t>(h->max_slots) * 2 * h->xbuf_slot_floats * 4);
   alloc(reinterpret_cast<void**>(&h->xctr), h->max_slots * 4);
@@ -500,7 +508,7 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
   p.tm_acc0 = h->tm_acc0; p.tm_acc2 = h->tm_acc2; p.tm_h0 = h->tm_h0; p.tm_z = h->tm_z;
   p.pol_in_smem = h->pol_in_smem;
   // row-ownership exchange: selection modes only (every row has exactly one source model per step)
-  p.own_mode = (!h->big && c.n_models > 1 && !p.per_model && p.ext_actions == nullptr &&
+  p.own_mode = (c.n_models > 1 && !p.per_model && p.ext_actions == nullptr &&
                 (c.sam_mode == METRPO_SAM_STEP_RAND || c.sam_mode == METRPO_SAM_EPS_RAND) && !h->disable_own) ? 1 : 0;
   p.rec_stride = h->rec_stride;
   p.xbuf_stride = h->xbuf_slot_floats;

@@ -182,11 +182,14 @@ __device__ __forceinline__ void dbg_record(unsigned* dbg, uint32_t tag, uint32_t
   dbg[idx + 2] = why;    // 1 = timed out here, 2 = saw the abort flag here
   dbg[idx + 3] = threadIdx.x;
 }
+// sleep_ns > 0: back off between polls (roles whose wake-up latency is not critical must not steal
+// issue slots from the epilogue warps that share their SM sub-partition)
 __device__ __noinline__ bool wait_bar_slow(uint64_t* bar, uint32_t parity, unsigned* dbg, uint32_t tag,
-                                           uint32_t info) {
+                                           uint32_t info, uint32_t sleep_ns = 0) {
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (sleep_ns) __nanosleep(sleep_ns);
     if ((++spins & 0xff) == 0) {
       if (*reinterpret_cast<volatile unsigned*>(dbg) != 0u) { dbg_record(dbg, tag, info, 2); return false; }
       if (globaltimer_ns() - t0 > METRPO_WAIT_TIMEOUT_NS) {
@@ -199,9 +202,9 @@ __device__ __noinline__ bool wait_bar_slow(uint64_t* bar, uint32_t parity, unsig
   return true;
 }
 __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, unsigned* dbg, uint32_t tag,
-                                         uint32_t info) {
+                                         uint32_t info, uint32_t sleep_ns = 0) {
   if (mbar_try_wait(bar, parity)) return true;
-  return wait_bar_slow(bar, parity, dbg, tag, info);
+  return wait_bar_slow(bar, parity, dbg, tag, info, sleep_ns);
 }
 __device__ __noinline__ bool wait_ge(const unsigned* ptr, unsigned target, unsigned* dbg, uint32_t tag,
                                      uint32_t info) {
@@ -222,6 +225,14 @@ __device__ __noinline__ bool wait_ge(const unsigned* ptr, unsigned target, unsig
 }
 #define WAITB(idx, par) \
   do { if (!wait_bar(&bars[idx], (par), p.dbg, (idx), (uint32_t)st_dbg)) goto bail; } while (0)
+#ifndef METRPO_PRODUCER_SLEEP_NS
+#define METRPO_PRODUCER_SLEEP_NS 0
+#endif
+#ifndef METRPO_MMA_PROLOGUE_SLEEP_NS
+#define METRPO_MMA_PROLOGUE_SLEEP_NS 0
+#endif
+#define WAITB_P(idx, par) \
+  do { if (!wait_bar(&bars[idx], (par), p.dbg, (idx), (uint32_t)st_dbg, METRPO_PRODUCER_SLEEP_NS)) goto bail; } while (0)
 
 // optional event trace (dev tool, -DMETRPO_TRACE): role-private logs of (code << 40 | clock) for
 // one CTA and a window of steps.  role 0 producer, 1 MMA, 2 epilogue.
@@ -371,11 +382,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
   __shared__ int abort_smem;
   // row-ownership mode (narrow instantiation only): compacted row list, per-row policy noise of
   // the next step, hidden activations of one policy pass (32 rows x 4 threads)
-  constexpr int OWN_ON = (SMAX <= 32) ? 1 : 0;
-  __shared__ int sList[OWN_ON ? TILE_M : 1];
+  // The narrow instantiation keeps them in static shared memory (its scratch area is only 16 KB);
+  // the wide one carves them out of its large policy scratch area (see below).
+  constexpr bool NARROW = (SMAX <= 32);
+  constexpr int OWN_TPR = NARROW ? 2 : 16;            // threads per owned row in the policy pass
+  constexpr int OWN_RPP = TILE_M / OWN_TPR;           // rows per pass
+  constexpr int OWN_HS = (NARROW ? HPB : HPMAX) + 1;  // row stride of the hidden activations
+  constexpr int OWN_OPTO = NARROW ? 4 : 2;            // outputs per thread of the last layer
+  __shared__ int sList[TILE_M];
   __shared__ int sCnt[4];
-  __shared__ __align__(16) float sEpsRow[OWN_ON ? TILE_M * AMAX : 4];
-  __shared__ float sHid[OWN_ON ? 2 * 64 * 33 : 1];
+  __shared__ __align__(16) float sEpsStatic[NARROW ? TILE_M * AMAX : 4];
+  __shared__ __align__(16) float sHidStatic[NARROW ? 2 * OWN_RPP * OWN_HS : 4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slot = blockIdx.x / p.K, k = blockIdx.x % p.K;
@@ -453,7 +470,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
   do {                                                                                        \
     if (wg < total_groups) {                                                                  \
       const uint32_t ws = wg & 1;                                                             \
-      if (wg >= 2) WAITB(B_ACC0FULL + ws, ((wg >> 1) - 1) & 1);                               \
+      if (wg >= 2) WAITB_P(B_ACC0FULL + ws, ((wg >> 1) - 1) & 1);                             \
       mbar_arrive_expect_tx(&bars[B_W0FULL + ws], p.w0g_bytes);                               \
       bulk_g2s_hint(sW0g + ws * p.w0g_bytes,                                                  \
                     wm + p.off_w0g + static_cast<size_t>(wg % NG) * p.w0g_bytes, p.w0g_bytes, \
@@ -470,14 +487,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               st_dbg = (st << 8) | (nc * p.KC + kc);
               if ((kc & 1) == 0) LOAD_W0();
               TRACE(0, 0x100 | (nc * p.KC + kc));
-              WAITB(B_EMPTY + s, sphase ^ 1);
+              WAITB_P(B_EMPTY + s, sphase ^ 1);
               TRACE(0, 0x200 | (nc * p.KC + kc));
               mbar_arrive_expect_tx(&bars[B_FULL + s], p.stage_bytes);
               bulk_g2s_hint(sStage + s * p.stage_bytes, src, p.stage_bytes, &bars[B_FULL + s], pol);
               src += p.stage_bytes;
               if (++s == NSTAGE) { s = 0; sphase ^= 1; }
               if (kc == w2_at) {
-                WAITB(B_W2EMPTY, (w2n & 1) ^ 1);
+                WAITB_P(B_W2EMPTY, (w2n & 1) ^ 1);
                 mbar_arrive_expect_tx(&bars[B_W2FULL], p.w2chunk_bytes);
                 bulk_g2s_hint(sW2, wm + p.off_w2 + static_cast<size_t>(nc) * p.w2chunk_bytes,
                               p.w2chunk_bytes, &bars[B_W2FULL], pol);
@@ -552,9 +569,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
         for (int st = 0; st < total_steps; ++st) {
           TRACE_ON(lane == 0 && st >= p.trace_t0 && st < p.trace_t1);
           TRACE(1, 0x1000);
-          // step prologue: Z ready, W0 tile of the step's first group, acc0 drained
-          WAITW4(B_ZREADY, zn & 1, B_W0FULL + (int)(gg & 1), (gg >> 1) & 1,
-                 gg > 0 ? B_ACC0FREE : -1, (gg - 1) & 1, -1, 0);
+          // step prologue: Z ready, W0 tile of the step's first group, acc0 drained (a ~20 k cycle
+          // wait for the epilogue's serial section: poll with back-off)
+          {
+            bool ok_ = true;
+            const int wi_ = lane == 0 ? B_ZREADY : lane == 1 ? B_W0FULL + (int)(gg & 1) : (lane == 2 && gg > 0) ? B_ACC0FREE : -1;
+            const uint32_t wp_ = lane == 0 ? (zn & 1) : lane == 1 ? ((gg >> 1) & 1) : ((gg - 1) & 1);
+            if (wi_ >= 0) ok_ = wait_bar(&bars[wi_], wp_, p.dbg, (uint32_t)wi_, (uint32_t)st_dbg, METRPO_MMA_PROLOGUE_SLEEP_NS);
+            if (!__all_sync(0xffffffffu, ok_)) goto bail;
+          }
           ++zn;
           TRACE(1, 0x1001);
           tc_fence_after();
@@ -683,6 +706,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
       const float* dMean = sNorm + 2 * p.SA;
       const float* dStd = sNorm + 2 * p.SA + S;
       float* scrA = sScr;
+      // own_mode buffers: [128 slots][slot_stride] policy inputs at scrA (shared with the Z staging
+      // rows), then -- wide instantiation -- the per-row noise and the hidden activations
+      float* sEpsRow = NARROW ? sEpsStatic : scrA + ((TILE_M * p.slot_stride + 3) & ~3);
+      float* sHid = NARROW ? sHidStatic : sEpsRow + TILE_M * AMAX;
+      const float* polW = NARROW ? static_cast<const float*>(sPolS) : sPol;
 
       uint32_t gg = 0, a1n = 0, a2n = 0, xn_cnt = 0;   // gg: L0 groups consumed so far
       float x[SMAX], a_raw[AMAX], a_mean[AMAX];
@@ -861,7 +889,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           tc_fence_before();
           mbar_arrive(&bars[B_ZREADY]);
           TRACE(2, 0x1001);
-          if constexpr (SMAX <= 32) {
+          {
             // own_mode: policy noise of step t+1 for this thread's row, parked in shared memory
             // (same thread reads it back at the end of the step if it owns the row)
             if (p.own_mode) {
@@ -999,7 +1027,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
             }
           }
           bool handled = false;
-          if constexpr (SMAX <= 32) {
+          {
             if (p.own_mode) {
               // ============ row-ownership exchange (step_rand / eps_rand) ============
               // Every CTA of the gang knows which model each row selects this step.  The CTA of
@@ -1065,6 +1093,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               }
               named_bar_sync(1, EPI_THREADS);
               TRACE(2, 0x1021);
+              if constexpr (NARROW) {
               // ---- policy of step t+1 for the owned rows: 2 threads per row, 64 rows per pass (one
               //      pass unless a CTA owns more than half of the tile) ----
               if (want_pol) {
@@ -1143,6 +1172,100 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                   }
                   __syncwarp();
                 }
+              }
+              } else {
+              // ---- policy of step t+1 for the owned rows: OWN_TPR threads per row (2: narrow policies,
+              //      64 rows per pass; 16: wide policies, 8 rows per pass), each thread a contiguous
+              //      block of npad / OWN_TPR output columns of every hidden layer ----
+              if (want_pol) {
+                const int part = e % OWN_TPR, jl = e / OWN_TPR;
+                const int nl = p.n_pol_layers;
+                for (int base = 0; base < n_own; base += OWN_RPP) {
+                  const int j = base + jl;
+                  const bool actv = j < n_own;
+                  const float* cur = scrA + (actv ? j : 0) * SPs;
+                  for (int l = 0; l < nl - 1; ++l) {
+                    const PolicyLayer& L = p.pl[l];
+                    const int opt = L.npad / OWN_TPR;       // 16 (narrow) | 8, 4, 2 (wide)
+                    float acc[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) acc[c] = (c < opt) ? polW[L.b_off + part * opt + c] : 0.f;
+                    const float* W = polW + L.w_off + part * opt;
+                    if (opt >= 4) {
+#pragma unroll 2
+                      for (int i = 0; i < L.nin; ++i) {
+                        const float xi = cur[i];
+                        const float4* w4 = reinterpret_cast<const float4*>(W + i * L.npad);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                          if (4 * q < opt) {
+                            const float4 w = w4[q];
+                            acc[4 * q] = __fmaf_rn(xi, w.x, acc[4 * q]); acc[4 * q + 1] = __fmaf_rn(xi, w.y, acc[4 * q + 1]);
+                            acc[4 * q + 2] = __fmaf_rn(xi, w.z, acc[4 * q + 2]); acc[4 * q + 3] = __fmaf_rn(xi, w.w, acc[4 * q + 3]);
+                          }
+                      }
+                    } else {
+#pragma unroll 4
+                      for (int i = 0; i < L.nin; ++i) {
+                        const float xi = cur[i];
+                        const float2 w = *reinterpret_cast<const float2*>(W + i * L.npad);
+                        acc[0] = __fmaf_rn(xi, w.x, acc[0]); acc[1] = __fmaf_rn(xi, w.y, acc[1]);
+                      }
+                    }
+                    float* out = sHid + (l & 1) * (OWN_RPP * OWN_HS) + jl * OWN_HS + part * opt;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                      if (c < opt) out[c] = fast_tanh(acc[c]);
+                    __syncwarp();
+                    cur = sHid + (l & 1) * (OWN_RPP * OWN_HS) + jl * OWN_HS;
+                  }
+                  const PolicyLayer& L = p.pl[nl - 1];
+                  const bool pact = part * OWN_OPTO < AMAX;
+                  float mo[OWN_OPTO];
+#pragma unroll
+                  for (int c = 0; c < OWN_OPTO; ++c) mo[c] = pact ? polW[L.b_off + OWN_OPTO * part + c] : 0.f;
+                  if (pact) {
+                    const float* W = polW + L.w_off + OWN_OPTO * part;
+#pragma unroll 4
+                    for (int i = 0; i < L.nin; ++i) {
+                      const float xi = cur[i];
+                      if constexpr (OWN_OPTO == 4) {
+                        const float4 w = *reinterpret_cast<const float4*>(W + i * AMAX);
+                        mo[0] = __fmaf_rn(xi, w.x, mo[0]); mo[1] = __fmaf_rn(xi, w.y, mo[1]);
+                        mo[2] = __fmaf_rn(xi, w.z, mo[2]); mo[3] = __fmaf_rn(xi, w.w, mo[3]);
+                      } else {
+                        const float2 w = *reinterpret_cast<const float2*>(W + i * AMAX);
+                        mo[0] = __fmaf_rn(xi, w.x, mo[0]); mo[1] = __fmaf_rn(xi, w.y, mo[1]);
+                      }
+                    }
+                  }
+                  if (p.pol_out_tanh) {
+#pragma unroll
+                    for (int c = 0; c < OWN_OPTO; ++c) mo[c] = tanhf(mo[c]);
+                  }
+                  if (actv && pact) {
+                    const int rowl = sList[j];
+                    const float* in = scrA + j * SPs;
+                    const size_t o = static_cast<size_t>(t + 1) * p.B + (tile * TILE_M + rowl);
+#pragma unroll
+                    for (int q = 0; q < OWN_OPTO; ++q) {
+                      const int c = OWN_OPTO * part + q;
+                      if (c < A) {
+                        const float mu = mo[q];
+                        float raw = mu;
+                        if (!p.determ) {   // a = eps * exp(log_std) + mean   (rllab get_actions)
+                          const float ls = fmaxf(polW[p.pol_logstd_off + c], -13.815510557964274f);
+                          raw = __fadd_rn(__fmul_rn(in[S + c], expf(ls)), mu);
+                        }
+                        if (p.act) p.act[o * A + c] = raw;
+                        if (p.mean) p.mean[o * A + c] = mu;
+                        rec[rowl * RS + c] = raw;
+                      }
+                    }
+                  }
+                  __syncwarp();
+                }
+              }
               }
               TRACE(2, 0x1022);
               // ---- publish / meet the gang: one release + one acquire poll per warp ----

@@ -81,6 +81,7 @@ __device__ __forceinline__ void layer_forward(const float* __restrict__ W, const
     float acc[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) acc[q] = (j0 + q < nout) ? b[j0 + q] : 0.f;
+#pragma unroll 4
     for (int i = 0; i < nin; ++i) {
       const float x = in[i * LD + n];
       const float4* w4 = reinterpret_cast<const float4*>(W + i * np + j0);
@@ -110,6 +111,7 @@ __device__ __forceinline__ void layer_tangent(const float* __restrict__ W, const
     float acc[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) acc[q] = (j0 + q < nout) ? vb[j0 + q] : 0.f;
+#pragma unroll 2
     for (int i = 0; i < nin; ++i) {
       const float x = a_in[i * LD + n];
       const float tx = t_in ? t_in[i * LD + n] : 0.f;
@@ -150,6 +152,7 @@ __device__ __forceinline__ void layer_backward_data(const float* __restrict__ W,
     float d[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) d[q] = (j0 + q < nout) ? d_out[(j0 + q) * LD + n] : 0.f;
+#pragma unroll 4
     for (int i = 0; i < nin; ++i) {
       const float4* w4 = reinterpret_cast<const float4*>(W + i * np + j0);
       float s = 0.f;
