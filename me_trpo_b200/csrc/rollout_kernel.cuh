@@ -385,10 +385,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
   // The narrow instantiation keeps them in static shared memory (its scratch area is only 16 KB);
   // the wide one carves them out of its large policy scratch area (see below).
   constexpr bool NARROW = (SMAX <= 32);
-  constexpr int OWN_TPR = NARROW ? 2 : 16;            // threads per owned row in the policy pass
+  constexpr int OWN_TPR = NARROW ? 2 : 8;             // threads per owned row in the policy pass
   constexpr int OWN_RPP = TILE_M / OWN_TPR;           // rows per pass
   constexpr int OWN_HS = (NARROW ? HPB : HPMAX) + 1;  // row stride of the hidden activations
-  constexpr int OWN_OPTO = NARROW ? 4 : 2;            // outputs per thread of the last layer
+  constexpr int OWN_OPTO = 4;                         // outputs per thread of the last layer
   __shared__ int sList[TILE_M];
   __shared__ int sCnt[4];
   __shared__ __align__(16) float sEpsStatic[NARROW ? TILE_M * AMAX : 4];
@@ -1175,7 +1175,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               }
               } else {
               // ---- policy of step t+1 for the owned rows: OWN_TPR threads per row (2: narrow policies,
-              //      64 rows per pass; 16: wide policies, 8 rows per pass), each thread a contiguous
+              //      64 rows per pass; 8: wide policies, 16 rows per pass), each thread a contiguous
               //      block of npad / OWN_TPR output columns of every hidden layer ----
               if (want_pol) {
                 const int part = e % OWN_TPR, jl = e / OWN_TPR;
@@ -1186,13 +1186,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                   const float* cur = scrA + (actv ? j : 0) * SPs;
                   for (int l = 0; l < nl - 1; ++l) {
                     const PolicyLayer& L = p.pl[l];
-                    const int opt = L.npad / OWN_TPR;       // 16 (narrow) | 8, 4, 2 (wide)
+                    const int opt = L.npad / OWN_TPR;       // 16, 8 or 4 output columns per thread
                     float acc[16];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) acc[c] = (c < opt) ? polW[L.b_off + part * opt + c] : 0.f;
                     const float* W = polW + L.w_off + part * opt;
-                    if (opt >= 4) {
-#pragma unroll 2
+                    {
+#pragma unroll 4
                       for (int i = 0; i < L.nin; ++i) {
                         const float xi = cur[i];
                         const float4* w4 = reinterpret_cast<const float4*>(W + i * L.npad);
@@ -1203,13 +1203,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                             acc[4 * q] = __fmaf_rn(xi, w.x, acc[4 * q]); acc[4 * q + 1] = __fmaf_rn(xi, w.y, acc[4 * q + 1]);
                             acc[4 * q + 2] = __fmaf_rn(xi, w.z, acc[4 * q + 2]); acc[4 * q + 3] = __fmaf_rn(xi, w.w, acc[4 * q + 3]);
                           }
-                      }
-                    } else {
-#pragma unroll 4
-                      for (int i = 0; i < L.nin; ++i) {
-                        const float xi = cur[i];
-                        const float2 w = *reinterpret_cast<const float2*>(W + i * L.npad);
-                        acc[0] = __fmaf_rn(xi, w.x, acc[0]); acc[1] = __fmaf_rn(xi, w.y, acc[1]);
                       }
                     }
                     float* out = sHid + (l & 1) * (OWN_RPP * OWN_HS) + jl * OWN_HS + part * opt;

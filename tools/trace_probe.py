@@ -9,6 +9,8 @@ from me_trpo_b200 import lib as L
 from oracle import models as om, envs as oe
 
 env, K, B, T, hidden = "half-cheetah", 5, 4096, 12, 1024
+if len(sys.argv) > 1:
+    env, K, B = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 spec = oe.ENV_SPECS[env]; S, A, drop = spec["S"], spec["A"], spec["drop"]
 rng = np.random.RandomState(0)
 models = om.init_dynamics(rng, S, A, drop, hidden, K); pol = om.init_policy(rng, S, spec["policy_hidden"], A)
