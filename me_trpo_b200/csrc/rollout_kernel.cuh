@@ -1174,89 +1174,69 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                 }
               }
               } else {
-              // ---- policy of step t+1 for the owned rows: OWN_TPR threads per row (2: narrow policies,
-              //      64 rows per pass; 8: wide policies, 16 rows per pass), each thread a contiguous
-              //      block of npad / OWN_TPR output columns of every hidden layer ----
+              // ---- wide policies: policy of step t+1 for the owned rows, 16 rows per pass.  The fp32
+              //      weights (64 KB for 100-50-25) do not fit in shared memory next to the operand
+              //      rings, so the CTA streams them from L2 ONCE per pass: thread c owns output column
+              //      c of the layer for all 16 rows (coalesced, independent weight loads, 8 in
+              //      flight), the 16 inputs of a row of W are read as four broadcast float4 from a
+              //      transposed activation tile [input][16 rows]. ----
               if (want_pol) {
-                const int part = e % OWN_TPR, jl = e / OWN_TPR;
                 const int nl = p.n_pol_layers;
-                for (int base = 0; base < n_own; base += OWN_RPP) {
-                  const int j = base + jl;
-                  const bool actv = j < n_own;
-                  const float* cur = scrA + (actv ? j : 0) * SPs;
-                  for (int l = 0; l < nl - 1; ++l) {
+                float* bufA = sHid;                       // [<=128 inputs][16 rows]
+                float* bufB = sHid + HPMAX * 16;
+                for (int base = 0; base < n_own; base += 16) {
+                  for (int q = e; q < 16 * S; q += EPI_THREADS) {   // transpose the pass's inputs
+                    const int rr = q / S, si = q - rr * S;
+                    bufA[si * 16 + rr] = (base + rr < n_own) ? scrA[(base + rr) * SPs + si] : 0.f;
+                  }
+                  named_bar_sync(1, EPI_THREADS);
+                  float* bin = bufA;
+                  float* bout = bufB;
+                  for (int l = 0; l < nl; ++l) {
                     const PolicyLayer& L = p.pl[l];
-                    const int opt = L.npad / OWN_TPR;       // 16, 8 or 4 output columns per thread
-                    float acc[16];
+                    const bool last = (l == nl - 1);
+                    if (e < L.npad) {
+                      float acc[16];
+                      const float bia = polW[L.b_off + e];
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) acc[c] = (c < opt) ? polW[L.b_off + part * opt + c] : 0.f;
-                    const float* W = polW + L.w_off + part * opt;
-                    {
-#pragma unroll 4
+                      for (int rr = 0; rr < 16; ++rr) acc[rr] = bia;
+                      const float* W = polW + L.w_off + e;
+#pragma unroll 8
                       for (int i = 0; i < L.nin; ++i) {
-                        const float xi = cur[i];
-                        const float4* w4 = reinterpret_cast<const float4*>(W + i * L.npad);
+                        const float w = W[i * L.npad];
+                        const float4* x4 = reinterpret_cast<const float4*>(bin + i * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                          const float4 xv = x4[q];
+                          acc[4 * q] = __fmaf_rn(xv.x, w, acc[4 * q]); acc[4 * q + 1] = __fmaf_rn(xv.y, w, acc[4 * q + 1]);
+                          acc[4 * q + 2] = __fmaf_rn(xv.z, w, acc[4 * q + 2]); acc[4 * q + 3] = __fmaf_rn(xv.w, w, acc[4 * q + 3]);
+                        }
+                      }
+                      if (!last) {
+                        float4* o4 = reinterpret_cast<float4*>(bout + e * 16);
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                          if (4 * q < opt) {
-                            const float4 w = w4[q];
-                            acc[4 * q] = __fmaf_rn(xi, w.x, acc[4 * q]); acc[4 * q + 1] = __fmaf_rn(xi, w.y, acc[4 * q + 1]);
-                            acc[4 * q + 2] = __fmaf_rn(xi, w.z, acc[4 * q + 2]); acc[4 * q + 3] = __fmaf_rn(xi, w.w, acc[4 * q + 3]);
+                          o4[q] = make_float4(fast_tanh(acc[4 * q]), fast_tanh(acc[4 * q + 1]), fast_tanh(acc[4 * q + 2]),
+                                              fast_tanh(acc[4 * q + 3]));
+                      } else if (e < A) {
+                        const float sg = p.determ ? 0.f : expf(fmaxf(polW[p.pol_logstd_off + e], -13.815510557964274f));
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr)
+                          if (base + rr < n_own) {
+                            const int rowl = sList[base + rr];
+                            const float mu = p.pol_out_tanh ? tanhf(acc[rr]) : acc[rr];
+                            float raw = mu;   // a = eps * exp(log_std) + mean   (rllab get_actions)
+                            if (!p.determ) raw = __fadd_rn(__fmul_rn(scrA[(base + rr) * SPs + S + e], sg), mu);
+                            const size_t o = static_cast<size_t>(t + 1) * p.B + (tile * TILE_M + rowl);
+                            if (p.act) p.act[o * A + e] = raw;
+                            if (p.mean) p.mean[o * A + e] = mu;
+                            rec[rowl * RS + e] = raw;
                           }
                       }
                     }
-                    float* out = sHid + (l & 1) * (OWN_RPP * OWN_HS) + jl * OWN_HS + part * opt;
-#pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                      if (c < opt) out[c] = fast_tanh(acc[c]);
-                    __syncwarp();
-                    cur = sHid + (l & 1) * (OWN_RPP * OWN_HS) + jl * OWN_HS;
+                    named_bar_sync(1, EPI_THREADS);
+                    float* tmp = bin; bin = bout; bout = tmp;
                   }
-                  const PolicyLayer& L = p.pl[nl - 1];
-                  const bool pact = part * OWN_OPTO < AMAX;
-                  float mo[OWN_OPTO];
-#pragma unroll
-                  for (int c = 0; c < OWN_OPTO; ++c) mo[c] = pact ? polW[L.b_off + OWN_OPTO * part + c] : 0.f;
-                  if (pact) {
-                    const float* W = polW + L.w_off + OWN_OPTO * part;
-#pragma unroll 4
-                    for (int i = 0; i < L.nin; ++i) {
-                      const float xi = cur[i];
-                      if constexpr (OWN_OPTO == 4) {
-                        const float4 w = *reinterpret_cast<const float4*>(W + i * AMAX);
-                        mo[0] = __fmaf_rn(xi, w.x, mo[0]); mo[1] = __fmaf_rn(xi, w.y, mo[1]);
-                        mo[2] = __fmaf_rn(xi, w.z, mo[2]); mo[3] = __fmaf_rn(xi, w.w, mo[3]);
-                      } else {
-                        const float2 w = *reinterpret_cast<const float2*>(W + i * AMAX);
-                        mo[0] = __fmaf_rn(xi, w.x, mo[0]); mo[1] = __fmaf_rn(xi, w.y, mo[1]);
-                      }
-                    }
-                  }
-                  if (p.pol_out_tanh) {
-#pragma unroll
-                    for (int c = 0; c < OWN_OPTO; ++c) mo[c] = tanhf(mo[c]);
-                  }
-                  if (actv && pact) {
-                    const int rowl = sList[j];
-                    const float* in = scrA + j * SPs;
-                    const size_t o = static_cast<size_t>(t + 1) * p.B + (tile * TILE_M + rowl);
-#pragma unroll
-                    for (int q = 0; q < OWN_OPTO; ++q) {
-                      const int c = OWN_OPTO * part + q;
-                      if (c < A) {
-                        const float mu = mo[q];
-                        float raw = mu;
-                        if (!p.determ) {   // a = eps * exp(log_std) + mean   (rllab get_actions)
-                          const float ls = fmaxf(polW[p.pol_logstd_off + c], -13.815510557964274f);
-                          raw = __fadd_rn(__fmul_rn(in[S + c], expf(ls)), mu);
-                        }
-                        if (p.act) p.act[o * A + c] = raw;
-                        if (p.mean) p.mean[o * A + c] = mu;
-                        rec[rowl * RS + c] = raw;
-                      }
-                    }
-                  }
-                  __syncwarp();
                 }
               }
               }
