@@ -1115,7 +1115,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                       }
                     }
                     const float* W = sPolS + L.w_off + 16 * part;
-#pragma unroll 2
+#pragma unroll 4
                     for (int i = 0; i < L.nin; ++i) {
                       const float xi = cur[i];
                       const float4* w4 = reinterpret_cast<const float4*>(W + i * HPB);
