@@ -65,6 +65,96 @@ __global__ void fit_gather_kernel(FitDims d, const float* __restrict__ x_data, c
   }
 }
 
+// Fused layer 0: gather + normalise + column drop + (z W0 + b0) + ReLU  (training.py:146-154,207-208,228).
+// The contraction is only Din (<= 88) deep, so it runs on the CUDA cores inside the pass that has to
+// write H0 anyway.  Block = 64 rows x 128 hidden columns of one model, 256 threads, 4 x 8 register
+// tile per thread; blockIdx.y == 0 also stores Z / XS / Y for the backward pass and the loss.
+constexpr int L0_ROWS = 64, L0_COLS = 128;
+__global__ void __launch_bounds__(256) fit_layer0_kernel(FitDims d, const float* __restrict__ x_data,
+                                                         const float* __restrict__ y_data, int n_data,
+                                                         const int* __restrict__ idx, int identity, int row0,
+                                                         unsigned long long seed, unsigned long long offset, int rows,
+                                                         const float* __restrict__ norm, const float* __restrict__ theta,
+                                                         float* __restrict__ Z, float* __restrict__ XS, float* __restrict__ Y,
+                                                         float* __restrict__ H0, long long strideZ, long long strideS,
+                                                         long long strideH) {
+  extern __shared__ __align__(16) float sm0[];
+  const int Dp = d.Din + 1;                    // odd-ish row stride of the z tile
+  float* zs = sm0;                             // [64][Dp]
+  float* ws = sm0 + ((L0_ROWS * Dp + 3) & ~3); // [Din][128]
+  __shared__ int sIdx[L0_ROWS];
+  const int tid = threadIdx.x, k = blockIdx.z, r0 = blockIdx.x * L0_ROWS, c0 = blockIdx.y * L0_COLS;
+  if (tid < L0_ROWS) {
+    const int r = r0 + tid;
+    int i = 0;
+    if (r < rows) {
+      if (identity) i = row0 + r;
+      else if (idx) i = idx[static_cast<size_t>(r) * d.K + k];
+      else i = philox_index(seed, static_cast<uint32_t>(offset), static_cast<uint32_t>(r * d.K + k), PHILOX_STREAM_FIT, n_data);
+      i = min(max(i, 0), n_data - 1);
+    }
+    sIdx[tid] = i;
+  }
+  // W0 tile [Din][128 columns of this block], coalesced float4
+  const float* W0 = theta + static_cast<size_t>(k) * d.P + d.oW0;
+  for (int q = tid; q < d.Din * (L0_COLS / 4); q += 256) {
+    const int i = q / (L0_COLS / 4), c4 = q - i * (L0_COLS / 4);
+    reinterpret_cast<float4*>(ws + i * L0_COLS)[c4] = *reinterpret_cast<const float4*>(W0 + static_cast<size_t>(i) * d.H + c0 + 4 * c4);
+  }
+  __syncthreads();
+  const float* in_mean = norm;
+  const float* in_std = norm + d.SA;
+  for (int q = tid; q < L0_ROWS * d.SA; q += 256) {
+    const int rr = q / d.SA, c = q - rr * d.SA, r = r0 + rr;
+    float zv = 0.f;
+    if (r < rows) {
+      const float v = x_data[static_cast<size_t>(sIdx[rr]) * d.SA + c];
+      zv = __fdiv_rn(__fsub_rn(v, in_mean[c]), in_std[c]);
+      if (blockIdx.y == 0) {
+        if (c >= d.drop) Z[k * strideZ + static_cast<size_t>(r) * d.Din + c - d.drop] = zv;
+        if (c < d.S) {
+          XS[k * strideS + static_cast<size_t>(r) * d.S + c] = v;
+          Y[k * strideS + static_cast<size_t>(r) * d.S + c] = y_data[static_cast<size_t>(sIdx[rr]) * d.S + c];
+        }
+      }
+    }
+    if (c >= d.drop) zs[rr * Dp + c - d.drop] = zv;
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;   // rows 4ty..4ty+3, columns 8tx..8tx+7
+  float acc[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[a][c] = 0.f;
+#pragma unroll 2
+  for (int i = 0; i < d.Din; ++i) {
+    const float4 w0 = *reinterpret_cast<const float4*>(ws + i * L0_COLS + 8 * tx);
+    const float4 w1 = *reinterpret_cast<const float4*>(ws + i * L0_COLS + 8 * tx + 4);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float z = zs[(4 * ty + a) * Dp + i];
+      acc[a][0] = fmaf(z, w0.x, acc[a][0]); acc[a][1] = fmaf(z, w0.y, acc[a][1]);
+      acc[a][2] = fmaf(z, w0.z, acc[a][2]); acc[a][3] = fmaf(z, w0.w, acc[a][3]);
+      acc[a][4] = fmaf(z, w1.x, acc[a][4]); acc[a][5] = fmaf(z, w1.y, acc[a][5]);
+      acc[a][6] = fmaf(z, w1.z, acc[a][6]); acc[a][7] = fmaf(z, w1.w, acc[a][7]);
+    }
+  }
+  const float* b0 = theta + static_cast<size_t>(k) * d.P + d.ob0 + c0 + 8 * tx;
+  const float4 bb0 = *reinterpret_cast<const float4*>(b0), bb1 = *reinterpret_cast<const float4*>(b0 + 4);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int r = r0 + 4 * ty + a;
+    if (r < rows) {
+      float4* o = reinterpret_cast<float4*>(H0 + k * strideH + static_cast<size_t>(r) * d.H + c0 + 8 * tx);
+      o[0] = make_float4(fmaxf(acc[a][0] + bb0.x, 0.f), fmaxf(acc[a][1] + bb0.y, 0.f), fmaxf(acc[a][2] + bb0.z, 0.f),
+                         fmaxf(acc[a][3] + bb0.w, 0.f));
+      o[1] = make_float4(fmaxf(acc[a][4] + bb1.x, 0.f), fmaxf(acc[a][5] + bb1.y, 0.f), fmaxf(acc[a][6] + bb1.z, 0.f),
+                         fmaxf(acc[a][7] + bb1.w, 0.f));
+    }
+  }
+}
+
 // H = relu(H + b)  (training.py:207-208), float4 over [K][rows][Hd]
 __global__ void fit_bias_relu_kernel(float* __restrict__ Hbuf, const float* __restrict__ theta, int b_off,
                                      long long P, int rows, int Hd, long long strideH) {
@@ -336,6 +426,11 @@ extern "C" int metrpo_fit_create(const metrpo_fit_cfg* cfg, metrpo_fit_t** out) 
     fit_free(h);
     return set_error(e == cudaErrorMemoryAllocation ? METRPO_ERR_NOMEM : METRPO_ERR_CUDA, "fit_create: %s", cudaGetErrorString(e));
   }
+  {
+    const size_t smem0 = (static_cast<size_t>((L0_ROWS * (d.Din + 1) + 3) & ~3) + static_cast<size_t>(d.Din) * L0_COLS) * 4;
+    if (smem0 > 48 * 1024)
+      cudaFuncSetAttribute(fit_layer0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem0));
+  }
   if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) {
     fit_free(h);
     return set_error(METRPO_ERR_CUDA, "fit_create: cublasCreate failed");
@@ -440,14 +535,19 @@ static int fit_forward(metrpo_fit* h, const float* x, const float* y, int n_data
                        int& launches) {
   const FitDims& d = h->d;
   const long long R = h->R, sZ = R * d.Din, sS = R * d.S, sH = R * d.H, P = d.P;
-  {
+  const int eb = static_cast<int>(std::min<long long>((static_cast<long long>(rows) * d.H / 4 + 255) / 256, 1184));
+  if (d.H % L0_COLS == 0) {
+    const size_t smem0 = (static_cast<size_t>((L0_ROWS * (d.Din + 1) + 3) & ~3) + static_cast<size_t>(d.Din) * L0_COLS) * 4;
+    fit_layer0_kernel<<<dim3((rows + L0_ROWS - 1) / L0_ROWS, d.H / L0_COLS, d.K), 256, smem0, st>>>(
+        d, x, y, n_data, idx, identity, row0, seed, offset, rows, h->norm, h->theta, h->Z, h->XS, h->Y, h->H0, sZ, sS, sH);
+    launches -= 2;
+  } else {   // hidden widths that are not a multiple of 128: gather, cuBLAS GEMM, bias + ReLU
     dim3 blk(32, 8), grd((rows + 7) / 8, d.K);
     fit_gather_kernel<<<grd, blk, 0, st>>>(d, x, y, n_data, idx, identity, row0, seed, offset, rows, h->norm,
                                           h->Z, h->XS, h->Y, sZ, sS);
+    METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.H, d.Din, h->Z, d.Din, sZ, h->theta + d.oW0, d.H, P, h->H0, d.H, sH));
+    fit_bias_relu_kernel<<<dim3(eb, d.K), 256, 0, st>>>(h->H0, h->theta, d.ob0, P, rows, d.H, sH);
   }
-  METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.H, d.Din, h->Z, d.Din, sZ, h->theta + d.oW0, d.H, P, h->H0, d.H, sH));
-  const int eb = static_cast<int>(std::min<long long>((static_cast<long long>(rows) * d.H / 4 + 255) / 256, 1184));
-  fit_bias_relu_kernel<<<dim3(eb, d.K), 256, 0, st>>>(h->H0, h->theta, d.ob0, P, rows, d.H, sH);
   METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.H, d.H, h->H0, d.H, sH, h->theta + d.oW1, d.H, P, h->H1, d.H, sH));
   fit_bias_relu_kernel<<<dim3(eb, d.K), 256, 0, st>>>(h->H1, h->theta, d.ob1, P, rows, d.H, sH);
   METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.S, d.H, h->H1, d.H, sH, h->theta + d.oW2, d.S, P, h->O, d.S, sS));
