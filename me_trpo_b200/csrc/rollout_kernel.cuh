@@ -1041,20 +1041,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               const bool own = valid && own_idx == k;
               const bool want_pol = (t + 1 < t1);
               TRACE(2, 0x1020);
+              float own_reward = 0.f;
+              bool own_dn = false;
               if (own) {
                 float u[AMAX];
 #pragma unroll
                 for (int i = 0; i < AMAX; ++i) u[i] = fminf(fmaxf(a_raw[i], -1.f), 1.f);
                 const float reward = -env_cost<SMAX, AMAX>(p.env_id, S, A, cand, u);   // env_helpers.py:601
                 const bool dn = env_is_done<SMAX>(p.env_id, S, cand) || (ts + 1 >= p.T_max);   // :603-604
-                const size_t o = static_cast<size_t>(t) * p.B + row;
-                if (p.obs) {
-#pragma unroll
-                  for (int s = 0; s < SMAX; ++s)
-                    if (s < S) p.obs[o * S + s] = x[s];
-                }
-                if (p.rew) p.rew[o] = reward;
-                if (p.done) p.done[o] = dn ? 1 : 0;
+                own_reward = reward; own_dn = dn;   // (trajectory stores happen after the release below)
                 if (dn) {   // :605-606 -> reset(dones)
                   const float* src = p.reset_pool + static_cast<size_t>((static_cast<long long>(nreset) * p.B + row) % p.R) * S;
 #pragma unroll
@@ -1244,11 +1239,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               // ---- publish / meet the gang: one release + one acquire poll per warp ----
               __syncwarp();
               int okw = 1;
-              if (lane == 0) {
-                red_release_gpu_add(&p.xctr[slot], 1u);
+              if (lane == 0) red_release_gpu_add(&p.xctr[slot], 1u);
+              if (own) {   // the owner's part of the trajectory record, off the gang's critical path
+                const size_t o = static_cast<size_t>(t) * p.B + row;
+                if (p.obs) {
+#pragma unroll
+                  for (int s = 0; s < SMAX; ++s)
+                    if (s < S) p.obs[o * S + s] = x[s];
+                }
+                if (p.rew) p.rew[o] = own_reward;
+                if (p.done) p.done[o] = own_dn ? 1 : 0;
+              }
+              if (lane == 0)
                 okw = wait_ge(&p.xctr[slot], 4u * static_cast<unsigned>(K) * (xn_cnt + 1), p.dbg, 101u,
                               (uint32_t)st_dbg) ? 1 : 0;
-              }
               okw = __shfl_sync(0xffffffffu, okw, 0);
               if (!okw) goto bail;
               TRACE(2, 0x1023);
