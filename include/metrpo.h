@@ -234,9 +234,10 @@ int metrpo_trpo_create(const metrpo_trpo_cfg* cfg, metrpo_trpo_t** out);
 int metrpo_trpo_destroy(metrpo_trpo_t* h);
 int metrpo_trpo_set_allreduce(metrpo_trpo_t* h, metrpo_allreduce_fn fn, void* user);
 /* Implementation of the per-sample pass (loss / gradient / Fisher-vector product):
- *   AUTO    the fastest measured one for the shape -- today SIMT (the legacy
- *           warp-level mma.sync path of sm_100a runs TF32 at only 2x the FP32 FMA rate)
- *   SIMT    fp32 FMA on CUDA cores (any shape)
+ *   AUTO    the fastest measured one for the shape: the register-tiled fp32 pass (csrc/trpo_tiled.cuh)
+ *           for policies whose layers are all <= 32 wide (every shipped params/*.json but
+ *           humanoid), else SIMT
+ *   SIMT    fp32 FMA on CUDA cores, one thread per sample (any shape)
  *   TF32    warp-level tensor-core MMAs, single TF32 products (10-bit operand mantissa); policies
  *           with <= 3 weight layers of width <= 32 (all shipped params/*.json but humanoid)
  *   TF32X3  same with 3xTF32 split products (fp32-equivalent accuracy) */

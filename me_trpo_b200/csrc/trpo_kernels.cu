@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(NT) policy_pass_kernel(const __grid_constant__
 
 }  // namespace metrpo
 #include "trpo_mma.cuh"
+#include "trpo_tiled.cuh"
 namespace metrpo {
 
 // ---------------------------------------------------------------------------------------------
@@ -975,8 +976,28 @@ static int launch_pass_mma(metrpo_trpo* h, const PassParams& p, cudaStream_t st)
   METRPO_CUDA_OK(cudaGetLastError());
   return METRPO_OK;
 }
+// register-tiled fp32 pass (trpo_tiled.cuh): persistent grid, 2 CTAs of 128 threads per SM
+template <int MODE>
+static int launch_pass_tiled(metrpo_trpo* h, const PassParams& p, cudaStream_t st) {
+  const size_t smem = tiled_smem_bytes(h->pd, MODE);
+  if (smem > static_cast<size_t>(h->max_smem)) return 1;
+  METRPO_CUDA_OK(cudaFuncSetAttribute(policy_pass_tiled_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  METRPO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, policy_pass_tiled_kernel<MODE>, TILED_NT, smem));
+  if (per_sm < 1) per_sm = 1;
+  const long long tiles = (p.N + TILED_NT - 1) / TILED_NT;
+  const int grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(h->num_sms) * per_sm));
+  policy_pass_tiled_kernel<MODE><<<grid, TILED_NT, smem, st>>>(p);
+  METRPO_CUDA_OK(cudaGetLastError());
+  return METRPO_OK;
+}
 template <int MODE>
 static int launch_pass(metrpo_trpo* h, const PassParams& p, cudaStream_t st) {
+  if (h->pass_impl == METRPO_TRPO_PASS_AUTO && tiled_eligible(h->pd)) {
+    const int rc = launch_pass_tiled<MODE>(h, p, st);
+    if (rc == METRPO_OK) { ++h->last_launches; return rc; }
+    if (rc != 1) return rc;
+  }
   if (h->pass_impl == METRPO_TRPO_PASS_TF32 || h->pass_impl == METRPO_TRPO_PASS_TF32X3) {
     if (!mma_eligible(h->pd))
       return set_error(METRPO_ERR_UNSUPPORTED, "trpo: the tensor-core pass covers <= 3 weight layers of width <= 32");
