@@ -9,10 +9,14 @@
 // parameter gradients (1 load per 2 FMAs): IPC ~0.2.  Here every dense layer of a 128-sample tile is
 // a small GEMM with a classic 2-D register tile: thread (sg, og) owns 8 consecutive samples x 4
 // consecutive outputs, so one step of the reduction is 3 shared-memory float4 loads (two of them
-// warp-broadcast) for 32 independent FMAs.  The parameter-gradient outer products use a 4 x 4
-// (input, output) tile per thread reduced over the 128 samples with float4 loads along the sample
-// axis (8 loads per 64 FMAs) and stay in registers for the whole kernel.  Activations keep the
-// [feature][sample] layout, so the per-sample likelihood / KL math is unchanged.
+// warp-broadcast) for 32 independent FMAs; layers with <= 8 outputs (the action layer) run one
+// thread per sample instead, so that no thread idles.  All deltas of a tile are produced first
+// (output delta in place of the mean rows, hidden deltas in the two scratch buffers); the
+// parameter-gradient outer products of ALL layers then run as ONE phase: the 4 x 4 (input, output)
+// tiles of every layer are dealt out over the 128 threads (120 tiles for 18-32-32-6), each reduced
+// over the 128 samples with float4 loads along the sample axis (8 loads per 64 FMAs) into registers
+// that live for the whole kernel; bias gradients are row sums of the delta buffers.  Activations keep
+// the [feature][sample] layout, so the per-sample likelihood / KL math is unchanged.
 #pragma once
 
 namespace metrpo {
@@ -23,7 +27,7 @@ constexpr int TILED_LD = TILED_NT + NTPAD;
 inline bool tiled_eligible(const PolDims& pd) {
   for (int i = 0; i <= pd.L; ++i)
     if (pd.d[i] > 32) return false;
-  return pd.L >= 1 && pd.L <= TP_MAXL;
+  return pd.L >= 1 && pd.L <= 3;   // deltas of <= 2 hidden layers live in the two scratch buffers
 }
 // transposed weights W^T[l]: [nout][pad4(nin)] (GRAD / FVP back-propagation of deltas)
 __host__ __device__ inline int tiled_wt_floats(const PolDims& pd) {
@@ -37,13 +41,15 @@ inline size_t tiled_smem_bytes(const PolDims& pd, int mode) {
   return fl * 4;
 }
 
-// c[p][q] += sum_k A[k][8 sg + p] * B[k][4 og + q]
+// c[p][q] += sum_k A[k][smp(p)] * B[k][4 og + q];  thread sg owns samples 4 sg + (0..3) and
+// 64 + 4 sg + (0..3): a quarter-warp then touches 8 consecutive float4 of a row (no bank conflicts
+// on loads or stores).  A already points at column 4 sg.
 __device__ __forceinline__ void tile_accum(float (&c)[8][4], const float* __restrict__ A, int K,
                                            const float* __restrict__ B, int ldb) {
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
     const float4 a0 = *reinterpret_cast<const float4*>(A + k * TILED_LD);
-    const float4 a1 = *reinterpret_cast<const float4*>(A + k * TILED_LD + 4);
+    const float4 a1 = *reinterpret_cast<const float4*>(A + k * TILED_LD + 64);
     const float4 w = *reinterpret_cast<const float4*>(B + k * ldb);
     const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
@@ -54,13 +60,29 @@ __device__ __forceinline__ void tile_accum(float (&c)[8][4], const float* __rest
   }
 }
 
+// per-sample evaluation of a layer with <= 8 outputs: c[j] += sum_k A[k][tid] * B[k][j]
+__device__ __forceinline__ void sample_accum(float (&c)[8], const float* __restrict__ A, int K,
+                                             const float* __restrict__ B, int ldb) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float a = A[k * TILED_LD];
+    const float4 w0 = *reinterpret_cast<const float4*>(B + k * ldb);
+    c[0] = fmaf(a, w0.x, c[0]); c[1] = fmaf(a, w0.y, c[1]); c[2] = fmaf(a, w0.z, c[2]); c[3] = fmaf(a, w0.w, c[3]);
+    if (ldb > 4) {
+      const float4 w1 = *reinterpret_cast<const float4*>(B + k * ldb + 4);
+      c[4] = fmaf(a, w1.x, c[4]); c[5] = fmaf(a, w1.y, c[5]); c[6] = fmaf(a, w1.z, c[6]); c[7] = fmaf(a, w1.w, c[7]);
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __grid_constant__ PassParams p) {
   constexpr int NT = TILED_NT, LD = TILED_LD;
   extern __shared__ __align__(16) float sm[];
   if (p.skip_flag != nullptr && *p.skip_flag != 0) return;
   const PolDims& pd = p.pd;
-  const int tid = threadIdx.x, sg = tid >> 3, og = tid & 7, L = pd.L, A = pd.d[L], S = pd.d[0];
+  const int tid = threadIdx.x, sg = tid & 15, og = tid >> 4, L = pd.L, A = pd.d[L], S = pd.d[0];
+  const int s0 = 4 * sg;   // this thread's samples: s0 .. s0+3 and 64+s0 .. 64+s0+3
   float* sW = sm;
   float* sV = sW + pd.P_pad;                                     // FVP only
   float* sWT = sV + (MODE == MODE_FVP ? pd.P_pad : 0);           // GRAD / FVP
@@ -101,13 +123,54 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
   if (tid < 32) sLs[tid] = tid < A ? p.theta[pd.logstd_off + tid] : 0.f;
   __syncthreads();
 
-  // parameter-gradient tiles owned by this thread: layer l, rows 4 ti .. (row nin = bias), cols 4 tj ..
-  float g[TP_MAXL][16];
-  float gls = 0.f;   // GRAD: log_std gradient entry `tid` (tid < A)
+  // delta at the OUTPUT of layer l: the mean rows for the last layer, then the scratch buffers
+  float* mu_rows = sAct + pd.act_row[L] * LD;
+  auto dbuf = [&](int l) -> float* { return l == L - 1 ? mu_rows : (l == L - 2 ? sBufA : sBufB); };
+
+  // ---- deal the 4 x 4 gradient tiles of all layers out over the threads (<= 2 per thread) ----
+  int it_l[2], it_i[2], it_j[2];
+  const float* it_a[2][4];
+  const float* it_d[2][4];
+  float g[2][16];
 #pragma unroll
-  for (int l = 0; l < TP_MAXL; ++l)
+  for (int s2 = 0; s2 < 2; ++s2) {
+    it_l[s2] = -1; it_i[s2] = 0; it_j[s2] = 0;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) g[l][q] = 0.f;
+    for (int q = 0; q < 16; ++q) g[s2][q] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { it_a[s2][q] = sZero; it_d[s2][q] = sZero; }
+    if (MODE != MODE_LOSS) {
+      int w = tid + NT * s2;
+      for (int l = 0; l < L; ++l) {
+        const int nin = pd.d[l], nout = pd.d[l + 1];
+        const int tiles_j = (nout + 3) >> 2, tiles_i = (nin + 3) >> 2;
+        if (w >= 0 && w < tiles_i * tiles_j) {
+          it_l[s2] = l; it_i[s2] = w / tiles_j; it_j[s2] = w - it_i[s2] * tiles_j;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            // strided tiles: a quarter-warp (same ti, 8 consecutive tj) reads 8 consecutive delta rows
+            const int i = it_i[s2] + tiles_i * q, j = it_j[s2] + tiles_j * q;
+            it_a[s2][q] = i < nin ? sAct + (pd.act_row[l] + i) * LD : sZero;
+            it_d[s2][q] = j < nout ? dbuf(l) + j * LD : sZero;
+          }
+          w = -1;
+        } else if (w >= 0) {
+          w -= tiles_i * tiles_j;
+        }
+      }
+    }
+  }
+  // bias gradient row owned by this thread: the tid-th output over all layers
+  int gb_l = -1, gb_j = 0;
+  const float* gb_row = sZero;
+  float gb = 0.f, gls = 0.f;   // gls: GRAD log_std gradient entry `tid` (tid < A)
+  if (MODE != MODE_LOSS) {
+    int w = tid;
+    for (int l = 0; l < L; ++l) {
+      if (w >= 0 && w < pd.d[l + 1]) { gb_l = l; gb_j = w; gb_row = dbuf(l) + w * LD; w = -1; }
+      else if (w >= 0) w -= pd.d[l + 1];
+    }
+  }
 
   double t_surr = 0.0, t_kl = 0.0, t_cnt = 0.0;
   const long long n_tiles = (p.N + NT - 1) / NT;
@@ -128,14 +191,23 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
       const int nin = pd.d[l], nout = pd.d[l + 1], np = pd.np[l];
-      if (4 * og < np) {
+      const bool use_tanh = (l < L - 1) || pd.out_tanh;
+      if (np <= 8) {          // one thread per sample
+        float c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = j < np ? sW[pd.sb_off[l] + j] : 0.f;
+        sample_accum(c, sAct + pd.act_row[l] * LD + tid, nin, sW + pd.sw_off[l], np);
+        float* out = sAct + pd.act_row[l + 1] * LD + tid;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nout) out[j * LD] = use_tanh ? tanh_fast(c[j]) : c[j];
+      } else if (4 * og < np) {
         float c[8][4];
         const float4 b = *reinterpret_cast<const float4*>(sW + pd.sb_off[l] + 4 * og);
 #pragma unroll
         for (int pp = 0; pp < 8; ++pp) { c[pp][0] = b.x; c[pp][1] = b.y; c[pp][2] = b.z; c[pp][3] = b.w; }
-        tile_accum(c, sAct + pd.act_row[l] * LD + 8 * sg, nin, sW + pd.sw_off[l] + 4 * og, np);
-        const bool use_tanh = (l < L - 1) || pd.out_tanh;
-        float* out = sAct + pd.act_row[l + 1] * LD + 8 * sg;
+        tile_accum(c, sAct + pd.act_row[l] * LD + s0, nin, sW + pd.sw_off[l] + 4 * og, np);
+        float* out = sAct + pd.act_row[l + 1] * LD + s0;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           if (4 * og + q < nout) {
@@ -144,32 +216,54 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
             for (int pp = 0; pp < 8; ++pp) v[pp] = use_tanh ? tanh_fast(c[pp][q]) : c[pp][q];
             float4* o4 = reinterpret_cast<float4*>(out + (4 * og + q) * LD);
             o4[0] = make_float4(v[0], v[1], v[2], v[3]);
-            o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+            o4[16] = make_float4(v[4], v[5], v[6], v[7]);
           }
       }
       __syncthreads();
     }
-    const float* mu = sAct + pd.act_row[L] * LD;
-    float* dOut = sBufA;   // delta at the output pre-activation, [A][LD]
+    const float* mu = mu_rows;
     float* cLs = sBufB;    // GRAD: per-sample d(-lr*adv)/d log_std_a, [A][LD]
 
     if (MODE == MODE_FVP) {
-      // tangent forward: t_out = (a_in V + vb + t_in W) * act'(a_out)
+      // tangent forward: t_out = (a_in V + vb + t_in W) * act'(a_out); the last layer's result, scaled
+      // by M = d^2 kl / d mu^2, is the output delta and replaces the mean rows
       const float* tin = nullptr;
 #pragma unroll 1
       for (int l = 0; l < L; ++l) {
         const int nin = pd.d[l], nout = pd.d[l + 1], np = pd.np[l];
-        float* tout = (l & 1) ? sBufB : sBufA;
         const bool last = (l == L - 1);
-        if (4 * og < np) {
+        float* tout = last ? mu_rows : ((l & 1) ? sBufB : sBufA);
+        const bool use_tanh = !last || pd.out_tanh;
+        if (np <= 8) {
+          float c[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) c[j] = j < np ? sV[pd.sb_off[l] + j] : 0.f;
+          sample_accum(c, sAct + pd.act_row[l] * LD + tid, nin, sV + pd.sw_off[l], np);
+          if (l > 0) sample_accum(c, tin + tid, nin, sW + pd.sw_off[l], np);
+          const float* aout = sAct + pd.act_row[l + 1] * LD + tid;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < nout) {
+              float v = c[j];
+              if (use_tanh) {
+                const float av = aout[j * LD];
+                v *= (1.f - av * av);
+                if (last) v *= (1.f - av * av);   // back through the output tanh as well
+              }
+              if (last) {
+                const float ls = fmaxf(sLs[j], -13.815510557964274f);
+                v *= (2.f / (2.f * __expf(2.f * ls) + 1e-8f)) * (ok ? 1.f : 0.f);   // kl_sym, A.3
+              }
+              tout[j * LD + tid] = v;
+            }
+        } else if (4 * og < np) {
           float c[8][4];
           const float4 b = *reinterpret_cast<const float4*>(sV + pd.sb_off[l] + 4 * og);
 #pragma unroll
           for (int pp = 0; pp < 8; ++pp) { c[pp][0] = b.x; c[pp][1] = b.y; c[pp][2] = b.z; c[pp][3] = b.w; }
-          tile_accum(c, sAct + pd.act_row[l] * LD + 8 * sg, nin, sV + pd.sw_off[l] + 4 * og, np);
-          if (l > 0) tile_accum(c, tin + 8 * sg, nin, sW + pd.sw_off[l] + 4 * og, np);
-          const bool use_tanh = !last || pd.out_tanh;
-          const float* aout = sAct + pd.act_row[l + 1] * LD + 8 * sg;
+          tile_accum(c, sAct + pd.act_row[l] * LD + s0, nin, sV + pd.sw_off[l] + 4 * og, np);
+          if (l > 0) tile_accum(c, tin + s0, nin, sW + pd.sw_off[l] + 4 * og, np);
+          const float* aout = sAct + pd.act_row[l + 1] * LD + s0;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             if (4 * og + q < nout) {
@@ -179,31 +273,29 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
               for (int pp = 0; pp < 8; ++pp) v[pp] = c[pp][q];
               if (use_tanh) {
                 const float4 a0 = *reinterpret_cast<const float4*>(aout + j * LD);
-                const float4 a1 = *reinterpret_cast<const float4*>(aout + j * LD + 4);
+                const float4 a1 = *reinterpret_cast<const float4*>(aout + j * LD + 64);
                 const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
                 for (int pp = 0; pp < 8; ++pp) v[pp] *= (1.f - av[pp] * av[pp]);
-                if (last) {   // back through the output tanh as well
+                if (last) {
 #pragma unroll
                   for (int pp = 0; pp < 8; ++pp) v[pp] *= (1.f - av[pp] * av[pp]);
                 }
               }
               if (last) {
-                // delta = M * mu_dot with M = d^2 kl / d mu^2 = 2 / (2 sigma^2 + 1e-8)   (kl_sym, A.3)
                 const float ls = fmaxf(sLs[j], -13.815510557964274f);
                 const float m = 2.f / (2.f * __expf(2.f * ls) + 1e-8f);
 #pragma unroll
-                for (int pp = 0; pp < 8; ++pp) v[pp] *= m * sOk[8 * sg + pp];
+                for (int pp = 0; pp < 8; ++pp) v[pp] *= m * sOk[(pp < 4 ? s0 : 60 + s0) + pp];
               }
-              float4* o4 = reinterpret_cast<float4*>(tout + j * LD + 8 * sg);
+              float4* o4 = reinterpret_cast<float4*>(tout + j * LD + s0);
               o4[0] = make_float4(v[0], v[1], v[2], v[3]);
-              o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+              o4[16] = make_float4(v[4], v[5], v[6], v[7]);
             }
         }
         __syncthreads();
         tin = tout;
       }
-      dOut = const_cast<float*>(tin);
       if (ok) t_cnt += 1.0;
     } else {
       // likelihood ratio and KL of this thread's sample (DiagonalGaussian, A.3)
@@ -234,9 +326,10 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
           if (a < A) {
             const float lsr = sLs[a];
             const float sgm = expf(fmaxf(lsr, -13.815510557964274f));
+            const float m = mu[a * LD + tid];
             float dv = cf * zn[a] / sgm;               // d ll / d mu = z / sigma
-            if (pd.out_tanh) { const float m = mu[a * LD + tid]; dv *= (1.f - m * m); }
-            dOut[a * LD + tid] = dv;
+            if (pd.out_tanh) dv *= (1.f - m * m);
+            mu_rows[a * LD + tid] = dv;                // output delta, in place of the mean (this thread's element)
             cLs[a * LD + tid] = (lsr > -13.815510557964274f) ? cf * (zn[a] * zn[a] - 1.f) : 0.f;   // d ll / d log_std
           }
         __syncthreads();
@@ -246,74 +339,68 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
           for (int q = 0; q < NT / 4; ++q) { const float4 v = r4[q]; s += (v.x + v.y) + (v.z + v.w); }
           gls += s;
         }
+        __syncthreads();   // cLs (sBufB) consumed before it may become a delta buffer
       }
     }
 
     if (MODE != MODE_LOSS) {
-      // ---- backward: outer products into the register tiles, deltas ping-pong between the buffers ----
-      if (MODE == MODE_GRAD) __syncthreads();   // cLs (sBufB) fully consumed before it becomes a delta buffer
-      float* dcur = dOut;
+      // ---- deltas of the hidden layers: d_in[i][n] = (sum_j d_out[j][n] W[i][j]) * (1 - a_in[i][n]^2) ----
+#pragma unroll 1
+      for (int l = L - 1; l >= 1; --l) {
+        const int nin = pd.d[l], nout = pd.d[l + 1], nip = (nin + 3) & ~3;
+        const float* dcur = dbuf(l);
+        float* dnext = dbuf(l - 1);
+        if (4 * og < nip) {
+          float c[8][4];
 #pragma unroll
-      for (int l = TP_MAXL - 1; l >= 0; --l)
-        if (l < L) {
-          const int nin = pd.d[l], nout = pd.d[l + 1];
-          const int tiles_j = (nout + 3) >> 2, tiles_i = (nin + 4) >> 2;   // rows 0..nin (row nin = bias)
-          if (tid < tiles_i * tiles_j) {
-            const int ti = tid / tiles_j, tj = tid - ti * tiles_j;
-            const float* ar[4];
-            const float* dr[4];
+          for (int pp = 0; pp < 8; ++pp) { c[pp][0] = 0.f; c[pp][1] = 0.f; c[pp][2] = 0.f; c[pp][3] = 0.f; }
+          tile_accum(c, dcur + s0, nout, sWT + wt_off[l] + 4 * og, nip);
+          const float* ain = sAct + pd.act_row[l] * LD + s0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * og + q < nin) {
+              const int i = 4 * og + q;
+              const float4 a0 = *reinterpret_cast<const float4*>(ain + i * LD);
+              const float4 a1 = *reinterpret_cast<const float4*>(ain + i * LD + 64);
+              float4* o4 = reinterpret_cast<float4*>(dnext + i * LD + s0);
+              o4[0] = make_float4(c[0][q] * (1.f - a0.x * a0.x), c[1][q] * (1.f - a0.y * a0.y),
+                                  c[2][q] * (1.f - a0.z * a0.z), c[3][q] * (1.f - a0.w * a0.w));
+              o4[16] = make_float4(c[4][q] * (1.f - a1.x * a1.x), c[5][q] * (1.f - a1.y * a1.y),
+                                  c[6][q] * (1.f - a1.z * a1.z), c[7][q] * (1.f - a1.w * a1.w));
+            }
+        }
+        __syncthreads();
+      }
+      // ---- parameter gradients of all layers in one phase ----
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2)
+        if (it_l[s2] >= 0) {
+#pragma unroll 2
+          for (int n4 = 0; n4 < NT / 4; ++n4) {
+            float4 av[4], dv[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const int i = 4 * ti + q, j = 4 * tj + q;
-              ar[q] = i < nin ? sAct + (pd.act_row[l] + i) * LD : (i == nin ? sOnes : sZero);
-              dr[q] = j < nout ? dcur + j * LD : sZero;
+              av[q] = *reinterpret_cast<const float4*>(it_a[s2][q] + 4 * n4);
+              dv[q] = *reinterpret_cast<const float4*>(it_d[s2][q] + 4 * n4);
             }
-#pragma unroll 2
-            for (int n4 = 0; n4 < NT / 4; ++n4) {
-              float4 av[4], dv[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                av[q] = *reinterpret_cast<const float4*>(ar[q] + 4 * n4);
-                dv[q] = *reinterpret_cast<const float4*>(dr[q] + 4 * n4);
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                float s = g[s2][4 * a + b];
+                s = fmaf(av[a].x, dv[b].x, s); s = fmaf(av[a].y, dv[b].y, s);
+                s = fmaf(av[a].z, dv[b].z, s); s = fmaf(av[a].w, dv[b].w, s);
+                g[s2][4 * a + b] = s;
               }
-#pragma unroll
-              for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                  float s = g[l][4 * a + b];
-                  s = fmaf(av[a].x, dv[b].x, s); s = fmaf(av[a].y, dv[b].y, s);
-                  s = fmaf(av[a].z, dv[b].z, s); s = fmaf(av[a].w, dv[b].w, s);
-                  g[l][4 * a + b] = s;
-                }
-            }
-          }
-          if (l > 0) {
-            // d_in[i][n] = (sum_j d_out[j][n] W[i][j]) * (1 - a_in[i][n]^2), via W^T rows [j][i]
-            const int nip = (nin + 3) & ~3;
-            float* dnext = (dcur == sBufA) ? sBufB : sBufA;
-            if (4 * og < nip) {
-              float c[8][4];
-#pragma unroll
-              for (int pp = 0; pp < 8; ++pp) { c[pp][0] = 0.f; c[pp][1] = 0.f; c[pp][2] = 0.f; c[pp][3] = 0.f; }
-              tile_accum(c, dcur + 8 * sg, nout, sWT + wt_off[l] + 4 * og, nip);
-              const float* ain = sAct + pd.act_row[l] * LD + 8 * sg;
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (4 * og + q < nin) {
-                  const int i = 4 * og + q;
-                  const float4 a0 = *reinterpret_cast<const float4*>(ain + i * LD);
-                  const float4 a1 = *reinterpret_cast<const float4*>(ain + i * LD + 4);
-                  float4* o4 = reinterpret_cast<float4*>(dnext + i * LD + 8 * sg);
-                  o4[0] = make_float4(c[0][q] * (1.f - a0.x * a0.x), c[1][q] * (1.f - a0.y * a0.y),
-                                      c[2][q] * (1.f - a0.z * a0.z), c[3][q] * (1.f - a0.w * a0.w));
-                  o4[1] = make_float4(c[4][q] * (1.f - a1.x * a1.x), c[5][q] * (1.f - a1.y * a1.y),
-                                      c[6][q] * (1.f - a1.z * a1.z), c[7][q] * (1.f - a1.w * a1.w));
-                }
-            }
-            __syncthreads();   // dnext complete; dcur's readers are done
-            dcur = dnext;
           }
         }
+      if (gb_l >= 0) {   // bias gradient: row sum of the delta buffer
+        const float4* r4 = reinterpret_cast<const float4*>(gb_row);
+        float s = 0.f;
+#pragma unroll 8
+        for (int q = 0; q < NT / 4; ++q) { const float4 v = r4[q]; s += (v.x + v.y) + (v.z + v.w); }
+        gb += s;
+      }
     }
     __syncthreads();   // tile buffers are reused by the next tile
   }
@@ -321,25 +408,20 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
   // ---- flush: register tiles -> global fp64 accumulators ----
   if (MODE != MODE_LOSS) {
 #pragma unroll
-    for (int l = 0; l < TP_MAXL; ++l)
-      if (l < L) {
-        const int nin = pd.d[l], nout = pd.d[l + 1];
-        const int tiles_j = (nout + 3) >> 2, tiles_i = (nin + 4) >> 2;
-        if (tid < tiles_i * tiles_j) {
-          const int ti = tid / tiles_j, tj = tid - ti * tiles_j;
+    for (int s2 = 0; s2 < 2; ++s2)
+      if (it_l[s2] >= 0) {
+        const int l = it_l[s2], nin = pd.d[l], nout = pd.d[l + 1];
+        const int tiles_j = (nout + 3) >> 2, tiles_i = (nin + 3) >> 2;
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int i = 4 * ti + a, j = 4 * tj + b;
-              const float v = g[l][4 * a + b];
-              if (j < nout && v != 0.f) {
-                if (i < nin) atomicAdd(&p.acc[pd.w_off[l] + i * nout + j], static_cast<double>(v));
-                else if (i == nin) atomicAdd(&p.acc[pd.b_off[l] + j], static_cast<double>(v));
-              }
-            }
-        }
+          for (int b = 0; b < 4; ++b) {
+            const int i = it_i[s2] + tiles_i * a, j = it_j[s2] + tiles_j * b;
+            const float v = g[s2][4 * a + b];
+            if (i < nin && j < nout && v != 0.f) atomicAdd(&p.acc[pd.w_off[l] + i * nout + j], static_cast<double>(v));
+          }
       }
+    if (gb_l >= 0 && gb != 0.f) atomicAdd(&p.acc[pd.b_off[gb_l] + gb_j], static_cast<double>(gb));
     if (MODE == MODE_GRAD && tid < A && gls != 0.f) atomicAdd(&p.acc[pd.logstd_off + tid], static_cast<double>(gls));
   }
   t_surr = warp_sum(t_surr); t_kl = warp_sum(t_kl); t_cnt = warp_sum(t_cnt);
