@@ -201,6 +201,46 @@ def run_cuda(args, rank, local_rank, world):
     total_ms_e2e, _, _ = timed(True)
     finite = bool(torch.isfinite(out["obs"]).all().item()) and bool(torch.isfinite(host_out["obs"]).all().item())
 
+    # The rest of the TRPO inner iteration on the trajectory of the last step (reported, not part of
+    # `value`): process_samples + baseline fit + natural-gradient update, all on the device.
+    trpo_info = None
+    try:
+        from me_trpo_b200.trpo import PolicyUpdate
+        pu = PolicyUpdate([spec["S"]] + list(spec["policy_hidden"]) + [spec["A"]], device=dev)
+        if world > 1:
+            pu.enable_allreduce()
+        parts = []
+        for W_, b_ in zip(pol["W"], pol["b"]):
+            parts += [W_.ravel(), b_.ravel()]
+        parts.append(pol["log_std"])
+        theta = torch.tensor(np.concatenate(parts).astype(np.float32), device=dev)
+        ls = torch.tensor(pol["log_std"], device=dev)
+        N = B_ROWS * T
+
+        def iteration():
+            pr = pu.process(out["obs"], out["rew"], out["done"], discount=1.0)
+            pu.fit_baseline(out["obs"], pr["ret"], pr["valid"], out["done"])
+            th = theta.clone()
+            return pu.update(th, out["obs"].reshape(N, -1), out["act"].reshape(N, -1), pr["adv"].reshape(N),
+                             out["mean"].reshape(N, -1), ls, valid=pr["valid"].reshape(N))
+        iteration()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        info = iteration()
+        e1.record()
+        barrier()
+        tms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        iv = info.cpu().numpy()
+        trpo_info = {"ms": float(tms.item()), "samples_per_gpu": N, "accepted": bool(iv[4] == 1.0),
+                     "mean_kl": float(iv[2]), "what": "process_samples + baseline fit + TRPO update (1 gradient, 11 "
+                     "Fisher-vector products, line search) on the last step's trajectory, device resident"}
+        pu.close()
+    except Exception as exc:   # reported, never fatal for the headline metric
+        trpo_info = {"error": repr(exc)}
+
     units_per_step = K_MODELS * B_ROWS * T * world
     value = units_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = units_per_step * args.steps / (total_ms_e2e * 1e-3)
@@ -243,7 +283,7 @@ def run_cuda(args, rank, local_rank, world):
                             "trajectory (obs, act, mean, rew, done) -> pinned host, copy of finished steps "
                             "overlapped with the remaining horizon (EnsembleRollout.run_to_host)" % E2E_CHUNKS},
             "gpu_launches": args.steps * ro.last_launches(),
-            "clocks": clocks, "finite": finite,
+            "clocks": clocks, "finite": finite, "trpo_half_of_iteration": trpo_info,
         }
         print(json.dumps(line), flush=True)
     ro.close()
