@@ -46,18 +46,27 @@ inline size_t tiled_smem_bytes(const PolDims& pd, int mode) {
 // on loads or stores).  A already points at column 4 sg.
 __device__ __forceinline__ void tile_accum(float (&c)[8][4], const float* __restrict__ A, int K,
                                            const float* __restrict__ B, int ldb) {
+  // packed FFMA2 (two fp32 FMAs per instruction, each IEEE-rounded like fmaf): on sm_100 the
+  // three-register scalar FFMA issues at half rate, the packed form restores the full FMA rate
+  float2 c2[8][2];
+#pragma unroll
+  for (int pp = 0; pp < 8; ++pp) { c2[pp][0] = make_float2(c[pp][0], c[pp][1]); c2[pp][1] = make_float2(c[pp][2], c[pp][3]); }
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
     const float4 a0 = *reinterpret_cast<const float4*>(A + k * TILED_LD);
     const float4 a1 = *reinterpret_cast<const float4*>(A + k * TILED_LD + 64);
     const float4 w = *reinterpret_cast<const float4*>(B + k * ldb);
     const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
 #pragma unroll
     for (int pp = 0; pp < 8; ++pp) {
-      c[pp][0] = fmaf(av[pp], w.x, c[pp][0]); c[pp][1] = fmaf(av[pp], w.y, c[pp][1]);
-      c[pp][2] = fmaf(av[pp], w.z, c[pp][2]); c[pp][3] = fmaf(av[pp], w.w, c[pp][3]);
+      const float2 aa = make_float2(av[pp], av[pp]);
+      c2[pp][0] = __ffma2_rn(aa, w01, c2[pp][0]);
+      c2[pp][1] = __ffma2_rn(aa, w23, c2[pp][1]);
     }
   }
+#pragma unroll
+  for (int pp = 0; pp < 8; ++pp) { c[pp][0] = c2[pp][0].x; c[pp][1] = c2[pp][0].y; c[pp][2] = c2[pp][1].x; c[pp][3] = c2[pp][1].y; }
 }
 
 // per-sample evaluation of a layer with <= 8 outputs: c[j] += sum_k A[k][tid] * B[k][j]
@@ -66,11 +75,16 @@ __device__ __forceinline__ void sample_accum(float (&c)[8], const float* __restr
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
     const float a = A[k * TILED_LD];
+    const float2 aa = make_float2(a, a);
     const float4 w0 = *reinterpret_cast<const float4*>(B + k * ldb);
-    c[0] = fmaf(a, w0.x, c[0]); c[1] = fmaf(a, w0.y, c[1]); c[2] = fmaf(a, w0.z, c[2]); c[3] = fmaf(a, w0.w, c[3]);
+    float2 r0 = __ffma2_rn(aa, make_float2(w0.x, w0.y), make_float2(c[0], c[1]));
+    float2 r1 = __ffma2_rn(aa, make_float2(w0.z, w0.w), make_float2(c[2], c[3]));
+    c[0] = r0.x; c[1] = r0.y; c[2] = r1.x; c[3] = r1.y;
     if (ldb > 4) {
       const float4 w1 = *reinterpret_cast<const float4*>(B + k * ldb + 4);
-      c[4] = fmaf(a, w1.x, c[4]); c[5] = fmaf(a, w1.y, c[5]); c[6] = fmaf(a, w1.z, c[6]); c[7] = fmaf(a, w1.w, c[7]);
+      r0 = __ffma2_rn(aa, make_float2(w1.x, w1.y), make_float2(c[4], c[5]));
+      r1 = __ffma2_rn(aa, make_float2(w1.z, w1.w), make_float2(c[6], c[7]));
+      c[4] = r0.x; c[5] = r0.y; c[6] = r1.x; c[7] = r1.y;
     }
   }
 }
@@ -386,11 +400,13 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-              for (int b = 0; b < 4; ++b) {
-                float s = g[s2][4 * a + b];
-                s = fmaf(av[a].x, dv[b].x, s); s = fmaf(av[a].y, dv[b].y, s);
-                s = fmaf(av[a].z, dv[b].z, s); s = fmaf(av[a].w, dv[b].w, s);
-                g[s2][4 * a + b] = s;
+              for (int b = 0; b < 4; b += 2) {
+                float2 s = make_float2(g[s2][4 * a + b], g[s2][4 * a + b + 1]);
+                s = __ffma2_rn(make_float2(av[a].x, av[a].x), make_float2(dv[b].x, dv[b + 1].x), s);
+                s = __ffma2_rn(make_float2(av[a].y, av[a].y), make_float2(dv[b].y, dv[b + 1].y), s);
+                s = __ffma2_rn(make_float2(av[a].z, av[a].z), make_float2(dv[b].z, dv[b + 1].z), s);
+                s = __ffma2_rn(make_float2(av[a].w, av[a].w), make_float2(dv[b].w, dv[b + 1].w), s);
+                g[s2][4 * a + b] = s.x; g[s2][4 * a + b + 1] = s.y;
               }
           }
         }
