@@ -275,7 +275,7 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     int scr_floats = (region_rows[0] + region_rows[1]) * TILE_M;
     if (h->big) {   // own_mode buffers of the wide instantiation live in the scratch area
       const int slot_stride = (c.state_dim + c.action_dim) | 1;
-      const int need = ((TILE_M * slot_stride + 3) & ~3) + TILE_M * h->amax + 2 * (TILE_M / 8) * (HPMAX + 1);
+      const int need = ((TILE_M * slot_stride + 3) & ~3) + TILE_M * h->amax + 2 * HPMAX * 16;   // inputs | noise | 2 x [<=128 inputs][16 rows]
       scr_floats = std::max(scr_floats, need);
     }
     h->off_scr = o; o += align_up(scr_floats * 4, 16);

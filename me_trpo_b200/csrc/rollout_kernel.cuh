@@ -380,19 +380,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint32_t tmem_slot;
   __shared__ int abort_smem;
-  // row-ownership mode (narrow instantiation only): compacted row list, per-row policy noise of
-  // the next step, hidden activations of one policy pass (32 rows x 4 threads)
-  // The narrow instantiation keeps them in static shared memory (its scratch area is only 16 KB);
-  // the wide one carves them out of its large policy scratch area (see below).
+  // row-ownership exchange: compacted row list, per-row policy noise of the next step, hidden
+  // activations of one policy pass.  The narrow instantiation keeps the last two in static shared
+  // memory (its scratch area is only 16 KB); the wide one carves them out of its policy scratch area.
   constexpr bool NARROW = (SMAX <= 32);
-  constexpr int OWN_TPR = NARROW ? 2 : 8;             // threads per owned row in the policy pass
-  constexpr int OWN_RPP = TILE_M / OWN_TPR;           // rows per pass
-  constexpr int OWN_HS = (NARROW ? HPB : HPMAX) + 1;  // row stride of the hidden activations
-  constexpr int OWN_OPTO = 4;                         // outputs per thread of the last layer
   __shared__ int sList[TILE_M];
   __shared__ int sCnt[4];
   __shared__ __align__(16) float sEpsStatic[NARROW ? TILE_M * AMAX : 4];
-  __shared__ __align__(16) float sHidStatic[NARROW ? 2 * OWN_RPP * OWN_HS : 4];
+  __shared__ __align__(16) float sHidStatic[NARROW ? 2 * 64 * 33 : 4];   // narrow: 2 layers x 64 rows x (32 + 1)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slot = blockIdx.x / p.K, k = blockIdx.x % p.K;
