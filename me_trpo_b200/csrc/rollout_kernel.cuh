@@ -359,8 +359,12 @@ __device__ __forceinline__ void relu_pack(const uint32_t (&v0)[32], const uint32
     if (kBias) {
       const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * c);
       const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * c + 4);
-      a[0] += b0.x; a[1] += b0.y; a[2] += b0.z; a[3] += b0.w;
-      a[4] += b1.x; a[5] += b1.y; a[6] += b1.z; a[7] += b1.w;
+      // packed FADD2 (the scalar three-operand form issues at half rate on sm_100)
+      const float2 r0 = __fadd2_rn(make_float2(a[0], a[1]), make_float2(b0.x, b0.y));
+      const float2 r1 = __fadd2_rn(make_float2(a[2], a[3]), make_float2(b0.z, b0.w));
+      const float2 r2 = __fadd2_rn(make_float2(a[4], a[5]), make_float2(b1.x, b1.y));
+      const float2 r3 = __fadd2_rn(make_float2(a[6], a[7]), make_float2(b1.z, b1.w));
+      a[0] = r0.x; a[1] = r0.y; a[2] = r1.x; a[3] = r1.y; a[4] = r2.x; a[5] = r2.y; a[6] = r3.x; a[7] = r3.y;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) pk[4 * c + i] = relu_pack_bf16x2(a[2 * i], a[2 * i + 1]);
@@ -1110,10 +1114,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                       const float xi = cur[i];
                       const float4* w4 = reinterpret_cast<const float4*>(W + i * HPB);
 #pragma unroll
+                      const float2 xx = make_float2(xi, xi);
+#pragma unroll
                       for (int q = 0; q < 4; ++q) {
                         const float4 w = w4[q];
-                        acc[4 * q] = __fmaf_rn(xi, w.x, acc[4 * q]); acc[4 * q + 1] = __fmaf_rn(xi, w.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = __fmaf_rn(xi, w.z, acc[4 * q + 2]); acc[4 * q + 3] = __fmaf_rn(xi, w.w, acc[4 * q + 3]);
+                        const float2 r0 = __ffma2_rn(xx, make_float2(w.x, w.y), make_float2(acc[4 * q], acc[4 * q + 1]));
+                        const float2 r1 = __ffma2_rn(xx, make_float2(w.z, w.w), make_float2(acc[4 * q + 2], acc[4 * q + 3]));
+                        acc[4 * q] = r0.x; acc[4 * q + 1] = r0.y; acc[4 * q + 2] = r1.x; acc[4 * q + 3] = r1.y;
                       }
                     }
                     float* out = sHid + (l & 1) * (64 * 33) + jl * 33 + 16 * part;
