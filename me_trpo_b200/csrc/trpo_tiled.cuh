@@ -69,6 +69,38 @@ __device__ __forceinline__ void tile_accum(float (&c)[8][4], const float* __rest
   for (int pp = 0; pp < 8; ++pp) { c[pp][0] = c2[pp][0].x; c[pp][1] = c2[pp][0].y; c[pp][2] = c2[pp][1].x; c[pp][3] = c2[pp][1].y; }
 }
 
+// two products sharing the A operand: cw += A * Bw, cv += A * Bv  (forward + tangent of one layer)
+__device__ __forceinline__ void tile_accum2(float (&cw)[8][4], float (&cv)[8][4], const float* __restrict__ A, int K,
+                                            const float* __restrict__ Bw, const float* __restrict__ Bv, int ldb) {
+  float2 w2[8][2], v2[8][2];
+#pragma unroll
+  for (int pp = 0; pp < 8; ++pp) {
+    w2[pp][0] = make_float2(cw[pp][0], cw[pp][1]); w2[pp][1] = make_float2(cw[pp][2], cw[pp][3]);
+    v2[pp][0] = make_float2(cv[pp][0], cv[pp][1]); v2[pp][1] = make_float2(cv[pp][2], cv[pp][3]);
+  }
+#pragma unroll 2
+  for (int k = 0; k < K; ++k) {
+    const float4 a0 = *reinterpret_cast<const float4*>(A + k * TILED_LD);
+    const float4 a1 = *reinterpret_cast<const float4*>(A + k * TILED_LD + 64);
+    const float4 w = *reinterpret_cast<const float4*>(Bw + k * ldb);
+    const float4 v = *reinterpret_cast<const float4*>(Bv + k * ldb);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
+    const float2 v01 = make_float2(v.x, v.y), v23 = make_float2(v.z, v.w);
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) {
+      const float2 aa = make_float2(av[pp], av[pp]);
+      w2[pp][0] = __ffma2_rn(aa, w01, w2[pp][0]); w2[pp][1] = __ffma2_rn(aa, w23, w2[pp][1]);
+      v2[pp][0] = __ffma2_rn(aa, v01, v2[pp][0]); v2[pp][1] = __ffma2_rn(aa, v23, v2[pp][1]);
+    }
+  }
+#pragma unroll
+  for (int pp = 0; pp < 8; ++pp) {
+    cw[pp][0] = w2[pp][0].x; cw[pp][1] = w2[pp][0].y; cw[pp][2] = w2[pp][1].x; cw[pp][3] = w2[pp][1].y;
+    cv[pp][0] = v2[pp][0].x; cv[pp][1] = v2[pp][0].y; cv[pp][2] = v2[pp][1].x; cv[pp][3] = v2[pp][1].y;
+  }
+}
+
 // per-sample evaluation of a layer with <= 8 outputs: c[j] += sum_k A[k][tid] * B[k][j]
 __device__ __forceinline__ void sample_accum(float (&c)[8], const float* __restrict__ A, int K,
                                              const float* __restrict__ B, int ldb) {
@@ -201,9 +233,9 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
       }
     }
     __syncthreads();
-    // ---- forward (training.py:99-103) ----
+    // ---- forward (training.py:99-103); in FVP mode it is fused with the tangent pass below ----
 #pragma unroll 1
-    for (int l = 0; l < L; ++l) {
+    for (int l = 0; l < (MODE == MODE_FVP ? 0 : L); ++l) {
       const int nin = pd.d[l], nout = pd.d[l + 1], np = pd.np[l];
       const bool use_tanh = (l < L - 1) || pd.out_tanh;
       if (np <= 8) {          // one thread per sample
@@ -239,8 +271,9 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
     float* cLs = sBufB;    // GRAD: per-sample d(-lr*adv)/d log_std_a, [A][LD]
 
     if (MODE == MODE_FVP) {
-      // tangent forward: t_out = (a_in V + vb + t_in W) * act'(a_out); the last layer's result, scaled
-      // by M = d^2 kl / d mu^2, is the output delta and replaces the mean rows
+      // forward and tangent of a layer in ONE phase (they share the layer input):
+      //   a_out = act(a_in W + b),   t_out = (a_in V + vb + t_in W) * act'(a_out);
+      // the last layer's tangent, scaled by M = d^2 kl / d mu^2, is the output delta (mean rows)
       const float* tin = nullptr;
 #pragma unroll 1
       for (int l = 0; l < L; ++l) {
@@ -249,46 +282,50 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
         float* tout = last ? mu_rows : ((l & 1) ? sBufB : sBufA);
         const bool use_tanh = !last || pd.out_tanh;
         if (np <= 8) {
-          float c[8];
+          float cf[8], c[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) c[j] = j < np ? sV[pd.sb_off[l] + j] : 0.f;
+          for (int j = 0; j < 8; ++j) { cf[j] = j < np ? sW[pd.sb_off[l] + j] : 0.f; c[j] = j < np ? sV[pd.sb_off[l] + j] : 0.f; }
+          sample_accum(cf, sAct + pd.act_row[l] * LD + tid, nin, sW + pd.sw_off[l], np);
           sample_accum(c, sAct + pd.act_row[l] * LD + tid, nin, sV + pd.sw_off[l], np);
           if (l > 0) sample_accum(c, tin + tid, nin, sW + pd.sw_off[l], np);
-          const float* aout = sAct + pd.act_row[l + 1] * LD + tid;
+          float* aout = sAct + pd.act_row[l + 1] * LD + tid;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (j < nout) {
               float v = c[j];
+              const float av = use_tanh ? tanh_fast(cf[j]) : cf[j];
               if (use_tanh) {
-                const float av = aout[j * LD];
                 v *= (1.f - av * av);
                 if (last) v *= (1.f - av * av);   // back through the output tanh as well
               }
               if (last) {
                 const float ls = fmaxf(sLs[j], -13.815510557964274f);
                 v *= (2.f / (2.f * __expf(2.f * ls) + 1e-8f)) * (ok ? 1.f : 0.f);   // kl_sym, A.3
+              } else {
+                aout[j * LD] = av;
               }
               tout[j * LD + tid] = v;
             }
         } else if (4 * og < np) {
-          float c[8][4];
+          float cf[8][4], c[8][4];
+          const float4 bw = *reinterpret_cast<const float4*>(sW + pd.sb_off[l] + 4 * og);
           const float4 b = *reinterpret_cast<const float4*>(sV + pd.sb_off[l] + 4 * og);
 #pragma unroll
-          for (int pp = 0; pp < 8; ++pp) { c[pp][0] = b.x; c[pp][1] = b.y; c[pp][2] = b.z; c[pp][3] = b.w; }
-          tile_accum(c, sAct + pd.act_row[l] * LD + s0, nin, sV + pd.sw_off[l] + 4 * og, np);
+          for (int pp = 0; pp < 8; ++pp) {
+            cf[pp][0] = bw.x; cf[pp][1] = bw.y; cf[pp][2] = bw.z; cf[pp][3] = bw.w;
+            c[pp][0] = b.x; c[pp][1] = b.y; c[pp][2] = b.z; c[pp][3] = b.w;
+          }
+          tile_accum2(cf, c, sAct + pd.act_row[l] * LD + s0, nin, sW + pd.sw_off[l] + 4 * og, sV + pd.sw_off[l] + 4 * og, np);
           if (l > 0) tile_accum(c, tin + s0, nin, sW + pd.sw_off[l] + 4 * og, np);
-          const float* aout = sAct + pd.act_row[l + 1] * LD + s0;
+          float* aout = sAct + pd.act_row[l + 1] * LD + s0;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             if (4 * og + q < nout) {
               const int j = 4 * og + q;
-              float v[8];
+              float v[8], av[8];
 #pragma unroll
-              for (int pp = 0; pp < 8; ++pp) v[pp] = c[pp][q];
+              for (int pp = 0; pp < 8; ++pp) { v[pp] = c[pp][q]; av[pp] = use_tanh ? tanh_fast(cf[pp][q]) : cf[pp][q]; }
               if (use_tanh) {
-                const float4 a0 = *reinterpret_cast<const float4*>(aout + j * LD);
-                const float4 a1 = *reinterpret_cast<const float4*>(aout + j * LD + 64);
-                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
                 for (int pp = 0; pp < 8; ++pp) v[pp] *= (1.f - av[pp] * av[pp]);
                 if (last) {
@@ -301,6 +338,10 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
                 const float m = 2.f / (2.f * __expf(2.f * ls) + 1e-8f);
 #pragma unroll
                 for (int pp = 0; pp < 8; ++pp) v[pp] *= m * sOk[(pp < 4 ? s0 : 60 + s0) + pp];
+              } else {
+                float4* a4 = reinterpret_cast<float4*>(aout + j * LD);
+                a4[0] = make_float4(av[0], av[1], av[2], av[3]);
+                a4[16] = make_float4(av[4], av[5], av[6], av[7]);
               }
               float4* o4 = reinterpret_cast<float4*>(tout + j * LD + s0);
               o4[0] = make_float4(v[0], v[1], v[2], v[3]);
