@@ -220,16 +220,20 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
 
   double t_surr = 0.0, t_kl = 0.0, t_cnt = 0.0;
   const long long n_tiles = (p.N + NT - 1) / NT;
+  const int obs_smp0 = tid / S, obs_f0 = tid - obs_smp0 * S, obs_dsmp = NT / S, obs_df = NT - obs_dsmp * S;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long n0 = tile * NT, ng = n0 + tid;
     const bool inb = ng < p.N;
     const bool ok = inb && (p.valid == nullptr || p.valid[ng] != 0);
     sOk[tid] = ok ? 1.f : 0.f;
-    {  // observations: coalesced read of the tile's [NT,S] block, stored [feature][sample]
+    {  // observations: coalesced read of the tile's [NT,S] block, stored [feature][sample]; element
+       // q = tid + NT*i maps to (sample, feature) = (q / S, q % S), advanced without divisions
       const long long base = n0 * S, lim = p.N * S;
+      int smp = obs_smp0, f = obs_f0;
       for (int q = tid; q < NT * S; q += NT) {
-        const int smp = q / S, f = q - smp * S;
         sAct[f * LD + smp] = (base + q < lim) ? p.obs[base + q] : 0.f;
+        smp += obs_dsmp; f += obs_df;
+        if (f >= S) { f -= S; ++smp; }
       }
     }
     __syncthreads();
@@ -356,8 +360,13 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
       // likelihood ratio and KL of this thread's sample (DiagonalGaussian, A.3)
       float ll_new = 0.f, ll_old = 0.f, kl = 0.f;
       float zn[32];
+      // blocks of 8 actions: whole blocks beyond A are skipped by a uniform branch (a fully
+      // unrolled, predicated 32-iteration loop would still issue all its instructions)
 #pragma unroll
-      for (int a = 0; a < 32; ++a)
+      for (int a0 = 0; a0 < 32; a0 += 8)
+       if (a0 < A) {
+#pragma unroll
+        for (int a = a0; a < a0 + 8; ++a)
         if (a < A) {
           const float m = mu[a * LD + tid];
           const float x = inb ? p.act[ng * A + a] : 0.f;
@@ -371,13 +380,17 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
           kl += ((om - m) * (om - m) + osg * osg - sgm * sgm) / (2.f * sgm * sgm + 1e-8f) + ls - ols;
           zn[a] = z;
         }
+       }
       const float lr = expf(ll_new - ll_old);
       const float ad = inb ? p.adv[ng] : 0.f;
       if (ok) { t_surr += static_cast<double>(lr) * ad; t_kl += kl; t_cnt += 1.0; }
       if (MODE == MODE_GRAD) {
         const float cf = ok ? -ad * lr : 0.f;       // d(-lr*adv)/d ll_new
 #pragma unroll
-        for (int a = 0; a < 32; ++a)
+        for (int a0 = 0; a0 < 32; a0 += 8)
+         if (a0 < A) {
+#pragma unroll
+          for (int a = a0; a < a0 + 8; ++a)
           if (a < A) {
             const float lsr = sLs[a];
             const float sgm = expf(fmaxf(lsr, -13.815510557964274f));
@@ -387,6 +400,7 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
             mu_rows[a * LD + tid] = dv;                // output delta, in place of the mean (this thread's element)
             cLs[a * LD + tid] = (lsr > -13.815510557964274f) ? cf * (zn[a] * zn[a] - 1.f) : 0.f;   // d ll / d log_std
           }
+         }
         __syncthreads();
         if (tid < A) {   // log_std entry tid: sum over the tile's samples
           const float4* r4 = reinterpret_cast<const float4*>(cLs + tid * LD);
