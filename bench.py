@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENV, K_MODELS, B_ROWS, HORIZON, HIDDEN = "half-cheetah", 5, 4096, 1000, 1024
-E2E_CHUNKS = 8
+E2E_CHUNKS = int(os.environ.get("METRPO_E2E_CHUNKS", "8"))
 METRIC = "simulated env steps/sec (ensemble x batch x horizon)"
 UNIT = "units/s"
 
