@@ -16,4 +16,8 @@ def run(ts, N, two, a_col, d_col, wait_each, reps=512):
 for N in (32, 128, 256):
     for w in (0, 1, 2, 3, 4, 7, 16):
         run(1, N, 0, 448, 0, w)
+# A from shared memory (SS form) and alternating accumulators, for comparison
+for N in (32, 128, 256):
+    run(0, N, 0, 448, 0, 0)
+    run(1, N, 1, 448, 0, 0)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "mma_bench3.json"), "w"), indent=1)
