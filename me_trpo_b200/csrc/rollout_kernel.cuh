@@ -186,13 +186,17 @@ __device__ __forceinline__ void dbg_record(unsigned* dbg, uint32_t tag, uint32_t
 // issue slots from the epilogue warps that share their SM sub-partition)
 __device__ __noinline__ bool wait_bar_slow(uint64_t* bar, uint32_t parity, unsigned* dbg, uint32_t tag,
                                            uint32_t info, uint32_t sleep_ns = 0) {
-  const uint64_t t0 = globaltimer_ns();
+  // the timer is first read after 256 failed polls: nearly every wait ends long before that, and
+  // a %globaltimer read at entry sits on the wake-up path of every wait that misses its first poll
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (sleep_ns) __nanosleep(sleep_ns);
     if ((++spins & 0xff) == 0) {
       if (*reinterpret_cast<volatile unsigned*>(dbg) != 0u) { dbg_record(dbg, tag, info, 2); return false; }
-      if (globaltimer_ns() - t0 > METRPO_WAIT_TIMEOUT_NS) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > METRPO_WAIT_TIMEOUT_NS) {
         atomicExch(dbg, 1u);
         dbg_record(dbg, tag, info, 1);
         return false;
