@@ -167,6 +167,21 @@ class data_collection:
     def get_num_data(self):
         return 0 if self.n_data is None else self.n_data
 
+    def get_next_batch(self, batch_size):
+        """utils.py:107-124: sequential window with wrap-around ('next_batch' sample_mode)."""
+        assert batch_size <= self.n_data, \
+            "Batch size %d is larger than n_data %d" % (batch_size, self.n_data)
+        start_idx, end_idx = self.cur_idx, self.cur_idx + batch_size
+        if end_idx > self.n_data:
+            head = batch_size - (self.n_data - start_idx)
+            idx = torch.cat([torch.arange(start_idx, self.n_data), torch.arange(0, head)])
+            self.cur_idx = head
+        else:
+            idx = torch.arange(start_idx, end_idx)
+            self.cur_idx = end_idx
+        idx = idx.to(self.device)
+        return self.x[idx], self.y[idx]
+
     def sample_indices(self, batch_size, rng=np.random):
         """Indices of `sample` (utils.py:129-131): uniform with replacement."""
         return np.floor(self.n_data * rng.uniform(0.0, 1.0, size=batch_size)).astype(np.int32)

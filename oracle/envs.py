@@ -2,7 +2,9 @@
 dimensions of the reference's imaginary environments.
 
 Restates, per env, `cost_np_vec` (per-row cost; reward = -cost, env_helpers.py:601) and `is_done`
-from the reference's env classes.  Only tests/, __graft_entry__.smoke() and bench.py's
+from the reference's env classes.  PINNED: tests/test_ref_fixtures.py compares every function
+here with the reference's own env classes (envs/com_*_env.py executed under shims) on inputs that
+exercise the clip / penalty / NaN branches.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs may import this package.
 
 Reference lines:

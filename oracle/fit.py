@@ -2,8 +2,9 @@
 dynamics fit -- build_dynamics_graph (model_based_rl.py:23-103), get_dynamics_optimizer
 (:154-183), optimize_models (:881-1051) and data_collection (utils.py:44-131).
 
-PARITY UNPINNED: the reference ships no tests / fixtures for this path and TensorFlow 1.4 cannot be
-imported here.  tf.train.AdamOptimizer's update rule is restated from its documentation
+PARITY: the prediction loss (build_dynamics_graph), get_ith_tensor and data_collection are PINNED
+against the reference's own code executed under shims (tests/test_ref_fixtures.py sections C, G).
+UNPINNED: the optimiser -- TensorFlow 1.4 cannot be imported here; tf.train.AdamOptimizer's update rule is restated from its documentation
 (lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t); theta -= lr_t * m / (sqrt(v) + epsilon));
 tests/test_fit_oracle.py pins the hand-written backward pass against torch.autograd in float64.
 """
@@ -172,6 +173,19 @@ class DataCollection:
 
     def get_num_data(self):
         return 0 if self.n_data is None else self.n_data
+
+    def get_next_batch(self, batch_size):
+        """utils.py:107-124: sequential window with wrap-around ('next_batch' sample_mode)."""
+        assert batch_size <= self.n_data, \
+            "Batch size %d is larger than n_data %d" % (batch_size, self.n_data)
+        start_idx, end_idx = self.cur_idx, self.cur_idx + batch_size
+        if end_idx > self.n_data:
+            indices = list(range(start_idx, self.n_data)) + list(range(0, batch_size - (self.n_data - start_idx)))
+            self.cur_idx = batch_size - (self.n_data - start_idx)
+        else:
+            indices = list(range(start_idx, end_idx))
+            self.cur_idx = end_idx
+        return self.x[indices, :], self.y[indices, :]
 
     def sample_indices(self, batch_size, rng):
         return np.floor(self.n_data * rng.uniform(0.0, 1.0, size=batch_size)).astype(np.intp)

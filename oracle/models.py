@@ -8,6 +8,9 @@ functions on the imaginary-rollout path.
   xavier_uniform     tf.contrib.layers.xavier_initializer() as used for W *and* b
                      (training.py:179,187-194)
 
+PINNED (round 2): dynamics_forward / policy_forward / RunningMeanStd are compared with the
+reference's own closures and class (training.py, running_mean_std.py executed under shims) in
+tests/test_ref_fixtures.py sections B and C.
 rllab's GaussianMLPPolicy is NOT vendored in the reference (README.md:7) -> its semantics here
 follow SURVEY.md Appendix A.1 ("parity unpinned" for that part).
 

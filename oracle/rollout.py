@@ -2,11 +2,12 @@
 rollout -- VecSimpleEnv (env_helpers.py:575-635) driven by VectorizedSampler.obtain_samples
 (samplers/vectorized_sampler.py:45-116) -- with every source of randomness made an explicit input.
 
-PARITY UNPINNED: the reference ships no tests / golden vectors for this path
-and its own TF1.4 + rllab + MuJoCo stack cannot be imported in this environment, so this
-restatement is checked only against the in-tree properties the reference states
-(`test_policy_cost` equivalence env_helpers.py:271-305, `|u| <= 1` asserts, T-consistency) and
-against a float64 evaluation of itself.
+PARITY PINNED (round 2): tests/test_ref_fixtures.py compares this module with
+tests/golden/ref_fixtures.npz, outputs of the REFERENCE'S OWN VecSimpleEnv / NeuralNetEnv /
+VectorizedSampler / build_policy_graph code executed in the build container under TF / rllab shims
+(tests/golden/make_ref_fixtures.py): all six sam_modes, timeouts, Ant's early termination with
+row-ordered reset consumption, the f64/f32 dtype drift.  What stays restated-from-memory is the
+part of rllab the reference does not vendor (GaussianMLPPolicy.get_actions).
 
 Randomness: the reference draws policy noise, per-step model indices and
 real-simulator reset states from one interleaved NumPy MT19937 stream; a device kernel cannot

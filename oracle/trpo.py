@@ -1,8 +1,11 @@
 """ORACLE (test infrastructure, not product code): float64 restatement of the TRPO half of the hot
 path -- sample processing and the natural-gradient policy update.
 
-PARITY UNPINNED: the arithmetic below lives in rllab (un-vendored, unpinned dependency of the
-reference, README.md:7,10) and is restated from SURVEY.md Appendix A.2-A.5; the reference ships no
+PARITY: process_samples and the surrogate / mean-KL composition are PINNED against the reference's
+own samplers/base.py and algos/npo.py executed under shims (tests/test_ref_fixtures.py section E).
+The arithmetic that lives in rllab (un-vendored, unpinned dependency of the reference,
+README.md:7,10: DiagonalGaussian, LinearFeatureBaseline, the ConjugateGradientOptimizer's CG /
+line search) is restated from SURVEY.md Appendix A.2-A.5 and stays UNPINNED; the reference ships no
 test vectors for it.  Call sites in the reference that fix the composition:
 
   process_samples           samples/base.py:48-182 (non-recurrent branch :74-105,167)
