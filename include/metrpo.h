@@ -186,28 +186,10 @@ int metrpo_rollout_get_trace(metrpo_rollout_t* h, unsigned long long* out_host);
 /* number of kernels the last run()/step() call launched on the stream (bench gpu_launches) */
 int metrpo_rollout_last_launches(const metrpo_rollout_t* h);
 
-/* Single-CTA tcgen05 GEMM self-test: C[128,N] = A[128,K] * B[N,K]^T (bf16 in, fp32 out) through
- * the same descriptors the rollout kernel uses.  mode 0: SW128 smem operands, B by bulk copy;
- * 1: no-swizzle core-matrix operands; 2: A in TMEM.  cycles (device, may be NULL) receives the
- * clock64 span of `reps` back-to-back K loops. */
-int metrpo_selftest_umma(int mode, int N, int K, int reps, const void* A_bf16, const void* B_bf16,
-                         float* C, unsigned long long* cycles, void* stream);
-
 /* Host-only helper (no CUDA call): the gang schedule the library builds for n_tiles row tiles of
  * 128 rows on n_slots gang slots over T steps; out receives n_slots * max_seg quadruples
  * (tile, t0, t1, wait_flag), tile == -1 for unused entries.  Returns max_seg (> 0) or a status. */
 int metrpo_debug_schedule(int n_tiles, int n_slots, int T, int32_t* out, int out_capacity_quads);
-
-/* Dev tool: tensor-pipe micro-benchmark.  Issues reps x 4 tcgen05.mma (M=128, K=16, given N) from
- * a warp-uniform loop; out_dev[0] = clock64 span of the issue loop, out_dev[1] = span until the
- * final commit is observed.  ts_mode 1: A operand from TMEM, 0: from shared memory. */
-int metrpo_bench_mma(int ts_mode, int N, int reps, int two_acc, int a_col, int d_col,
-                     int wait_each, unsigned long long* out_dev, void* stream);
-
-/* Dev tool: legacy warp-level tensor path (mma.sync) micro-benchmark.  `warps` warps of one CTA
- * issue reps x 8 independent MMAs each; kind 0: m16n8k8 tf32, 1: m16n8k16 bf16.  out_dev[0] =
- * clock64 span of warp 0. */
-int metrpo_bench_mma_sync(int kind, int warps, int reps, unsigned long long* out_dev, void* stream);
 
 /* =============================================================================================
  * TRPO half of the inner iteration: sample processing + natural-gradient policy update.

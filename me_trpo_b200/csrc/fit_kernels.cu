@@ -49,7 +49,7 @@ __global__ void fit_gather_kernel(FitDims d, const float* __restrict__ x_data, c
   int i;
   if (identity) i = row0 + r;
   else if (idx) i = idx[static_cast<size_t>(r) * d.K + k];
-  else i = philox_index(seed, static_cast<uint32_t>(offset), static_cast<uint32_t>(r * d.K + k), PHILOX_STREAM_FIT, n_data);
+  else i = philox_index(seed, static_cast<uint64_t>(offset), static_cast<uint32_t>(r * d.K + k), PHILOX_STREAM_FIT, n_data);
   i = min(max(i, 0), n_data - 1);
   const float* xr = x_data + static_cast<size_t>(i) * d.SA;
   const float* yr = y_data + static_cast<size_t>(i) * d.S;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) fit_layer0_kernel(FitDims d, const float*
     if (r < rows) {
       if (identity) i = row0 + r;
       else if (idx) i = idx[static_cast<size_t>(r) * d.K + k];
-      else i = philox_index(seed, static_cast<uint32_t>(offset), static_cast<uint32_t>(r * d.K + k), PHILOX_STREAM_FIT, n_data);
+      else i = philox_index(seed, static_cast<uint64_t>(offset), static_cast<uint32_t>(r * d.K + k), PHILOX_STREAM_FIT, n_data);
       i = min(max(i, 0), n_data - 1);
     }
     sIdx[tid] = i;

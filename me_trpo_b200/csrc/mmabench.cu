@@ -3,6 +3,7 @@
 // Operand contents are irrelevant (smem is left uninitialised); only timing is reported.
 #include "umma.cuh"
 #include "metrpo.h"
+#include "metrpo_dev.h"
 #include "common.cuh"
 
 namespace metrpo {

@@ -1,5 +1,8 @@
 // Counter-based Philox4x32-10 used when the caller passes no explicit noise tensors.
-// counter = (global step | episode, global row, stream, 'METR'), key = 64-bit seed.
+// counter = (low 32 bits of the global step | episode, global row, stream,
+// 'METR' ^ high 32 bits of the global step), key = 64-bit seed.  The step counter is 64 bits wide so
+// that callers spacing their launches by a fixed stride (VectorizedSampler: 2^20 per call) never
+// replay a stream, however long the run.
 // oracle/rollout.py implements the same integer pipeline; the Box-Muller transform there is
 // evaluated in float64 and rounded, here in fp32 (agreement ~1e-6).
 #pragma once
@@ -37,17 +40,19 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n0, 
 }
 
 // 4 N(0,1) values of block `blk` of a stream
-__device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t step, uint32_t row,
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t step, uint32_t row,
                                                uint32_t stream, float (&n)[4]) {
-  uint4 x = philox4x32_10(step, row, stream, PHILOX_C3, static_cast<uint32_t>(seed),
+  uint4 x = philox4x32_10(static_cast<uint32_t>(step), row, stream,
+                          PHILOX_C3 ^ static_cast<uint32_t>(step >> 32), static_cast<uint32_t>(seed),
                           static_cast<uint32_t>(seed >> 32));
   box_muller(x.x, x.y, n[0], n[1]);
   box_muller(x.z, x.w, n[2], n[3]);
 }
 
-__device__ __forceinline__ int philox_index(uint64_t seed, uint32_t counter, uint32_t row,
+__device__ __forceinline__ int philox_index(uint64_t seed, uint64_t counter, uint32_t row,
                                             uint32_t stream, int K) {
-  uint4 x = philox4x32_10(counter, row, stream, PHILOX_C3, static_cast<uint32_t>(seed),
+  uint4 x = philox4x32_10(static_cast<uint32_t>(counter), row, stream,
+                          PHILOX_C3 ^ static_cast<uint32_t>(counter >> 32), static_cast<uint32_t>(seed),
                           static_cast<uint32_t>(seed >> 32));
   return static_cast<int>(__umulhi(x.x, static_cast<uint32_t>(K)));
 }

@@ -738,7 +738,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
           for (int blk = 0; blk < AMAX / 4; ++blk) {
             float n4[4];
             if (blk * 4 < A)
-              philox_normal4(p.seed, static_cast<uint32_t>(p.offset + tt), static_cast<uint32_t>(row + p.row_offset),
+              philox_normal4(p.seed, p.offset + static_cast<unsigned long long>(tt), static_cast<uint32_t>(row + p.row_offset),
                              PHILOX_STREAM_EPS + blk, n4);
             else
               n4[0] = n4[1] = n4[2] = n4[3] = 0.f;
@@ -907,10 +907,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
               if (p.model_idx != nullptr)
                 own_idx = valid ? p.model_idx[static_cast<size_t>(t) * p.B + row] : 0;
               else if (p.sam_mode == METRPO_SAM_STEP_RAND)
-                own_idx = philox_index(p.seed, static_cast<uint32_t>(p.offset + t),
+                own_idx = philox_index(p.seed, p.offset + static_cast<unsigned long long>(t),
                                        static_cast<uint32_t>(row + p.row_offset), PHILOX_STREAM_IDX, K);
               else
-                own_idx = philox_index(p.seed, static_cast<uint32_t>(nreset),
+                own_idx = philox_index(p.seed, static_cast<uint64_t>(static_cast<uint32_t>(nreset)),
                                        static_cast<uint32_t>(row + p.row_offset), PHILOX_STREAM_EIDX, K);
               own_idx = min(max(own_idx, 0), K - 1);
             }
@@ -1346,10 +1346,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                 if (p.model_idx != nullptr)
                   idx = valid ? p.model_idx[static_cast<size_t>(t) * p.B + row] : 0;
                 else if (mode == METRPO_SAM_STEP_RAND)
-                  idx = philox_index(p.seed, static_cast<uint32_t>(p.offset + t),
+                  idx = philox_index(p.seed, p.offset + static_cast<unsigned long long>(t),
                                      static_cast<uint32_t>(row + p.row_offset), PHILOX_STREAM_IDX, K);
                 else
-                  idx = philox_index(p.seed, static_cast<uint32_t>(nreset),
+                  idx = philox_index(p.seed, static_cast<uint64_t>(static_cast<uint32_t>(nreset)),
                                      static_cast<uint32_t>(row + p.row_offset), PHILOX_STREAM_EIDX, K);
                 idx = min(max(idx, 0), K - 1);
               }
@@ -1375,7 +1375,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rollout_kernel(const __grid_co
                     nz = valid ? p.std_noise[(static_cast<size_t>(t) * p.B + row) * S + s] : 0.f;
                   } else {
                     float n4[4];
-                    philox_normal4(p.seed, static_cast<uint32_t>(p.offset + t),
+                    philox_normal4(p.seed, p.offset + static_cast<unsigned long long>(t),
                                    static_cast<uint32_t>(row + p.row_offset), PHILOX_STREAM_STD + (s >> 2), n4);
                     nz = n4[s & 3];
                   }

@@ -4,6 +4,7 @@
 // per-layout tensor-pipe cycle counts can be measured in isolation (reps > 1).
 #include "umma.cuh"
 #include "metrpo.h"
+#include "metrpo_dev.h"
 #include "common.cuh"
 
 namespace metrpo {

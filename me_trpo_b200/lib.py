@@ -76,9 +76,6 @@ _PROTOS = {
     "metrpo_rollout_set_trace": (_i, [_vp, _i, _i, _i]),
     "metrpo_rollout_get_trace": (_i, [_vp, _vp]),
     "metrpo_debug_schedule": (_i, [_i, _i, _i, _vp, _i]),
-    "metrpo_bench_mma": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
-    "metrpo_bench_mma_sync": (_i, [_i, _i, _i, _vp, _vp]),
-    "metrpo_selftest_umma": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "metrpo_trpo_create": (_i, [ctypes.POINTER(TrpoCfg), ctypes.POINTER(_vp)]),
     "metrpo_trpo_destroy": (_i, [_vp]),
     "metrpo_trpo_set_allreduce": (_i, [_vp, ALLREDUCE_FN, _vp]),
@@ -103,12 +100,23 @@ _PROTOS = {
     "metrpo_fit_restore_best": (_i, [_vp, _vp]),
 }
 
+# development library (include/metrpo_dev.h): descriptor self-test + issue-rate micro-benchmarks
+DEV_LIB_PATH = os.path.join(_HERE, "libmetrpo_dev.so")
+DEV_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "metrpo_dev.h")
+_DEV_PROTOS = {
+    "metrpo_last_error": (ctypes.c_char_p, []),
+    "metrpo_bench_mma": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "metrpo_bench_mma_sync": (_i, [_i, _i, _i, _vp, _vp]),
+    "metrpo_selftest_umma": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+}
+
 _lib = None
+_dev_lib = None
 
 
-def declared_symbols():
-    """Every function name include/metrpo.h declares."""
-    with open(HEADER_PATH) as f:
+def declared_symbols(header=None):
+    """Every function name include/metrpo.h (or the given header) declares."""
+    with open(header or HEADER_PATH) as f:
         text = f.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(metrpo_[a-z0-9_]+)\s*\(", text)))
@@ -132,6 +140,26 @@ def load():
     return lib
 
 
+def load_dev():
+    """dlopen the development library (self-test / micro-benchmarks); not used by the product."""
+    global _dev_lib
+    if _dev_lib is None:
+        if not os.path.exists(DEV_LIB_PATH):
+            raise RuntimeError("libmetrpo_dev.so is not built (%s). Run `python __graft_entry__.py`." % DEV_LIB_PATH)
+        lib = ctypes.CDLL(DEV_LIB_PATH)
+        for name, (res, args) in _DEV_PROTOS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _dev_lib = lib
+    return _dev_lib
+
+
+def check_dev(status, what=""):
+    if status != 0:
+        raise RuntimeError("%s failed (status %d): %s" % (what or "metrpo dev call", status,
+                                                        load_dev().metrpo_last_error().decode("utf-8", "replace")))
+
+
 def check_exports():
     """The library exports every symbol the header declares (CPU-only check, no compute)."""
     lib = load()
@@ -141,6 +169,14 @@ def check_exports():
     undeclared = [s for s in declared_symbols() if s not in _PROTOS]
     if undeclared:
         raise RuntimeError("lib.py has no prototype for: %s" % undeclared)
+    leaked = [s for s in _DEV_PROTOS if s != "metrpo_last_error" and hasattr(lib, s)]
+    if leaked:
+        raise RuntimeError("development symbols exported by the product library: %s" % leaked)
+    if os.path.exists(DEV_LIB_PATH):
+        dev = load_dev()
+        missing = [s for s in declared_symbols(DEV_HEADER_PATH) if not hasattr(dev, s)]
+        if missing:
+            raise RuntimeError("libmetrpo_dev.so lacks symbols declared in metrpo_dev.h: %s" % missing)
     return declared_symbols()
 
 

@@ -174,19 +174,48 @@ def optimize_policy(algo, policy_opt_params, policy_validation_init, logger=None
 # ================================================================================================
 # Outer loop: collect -> fit the ensemble -> improve the policy  (model_based_rl.py:231-755)
 # ================================================================================================
-def sample_trajectories(real_env, policy, exploration, batch_size, max_timestep, rng, logger=None):
-    """env_helpers.py:352-460 without parameter-space noise (prepare_policy perturbs TF variables
-    between episodes; exploration here is the action noise only -- real-environment collection is
-    outside the hot path).  Returns (Os, As, Rs, info)."""
+def prepare_policy(W, b, param_noise, diff_weights, initial_param_std, rng):
+    """env_helpers.py:50-59: per-episode parameter-space exploration.  Returns perturbed COPIES of
+    the mean-network weights -- flat_weight_update = param_noise * diff_weights * randn(n), applied
+    to the biases then the weight matrices (the reference's flat order, model_based_rl.py:419-421;
+    log_std is not perturbed) -- and mean(|update|).  `diff_weights` maps like
+    policy.get_param_values(): (W, b) per layer, then log_std (ignored)."""
+    if diff_weights is None:
+        assert initial_param_std == 0.0
+        return W, b, 0.0
+    dW, db, o = [], [], 0
+    for w, v in zip(W, b):
+        dW.append(np.asarray(diff_weights[o:o + w.size]).reshape(w.shape)); o += w.size
+        db.append(np.asarray(diff_weights[o:o + v.size])); o += v.size
+    n_vars = sum(v.size for v in b) + sum(w.size for w in W)
+    z = rng.randn(n_vars)
+    W2, b2, o, total = [], [], 0, 0.0
+    for v, d in zip(b, db):
+        upd = param_noise * d * z[o:o + v.size]; o += v.size
+        b2.append(v + upd); total += np.abs(upd).sum()
+    for w, d in zip(W, dW):
+        upd = param_noise * d * z[o:o + w.size].reshape(w.shape); o += w.size
+        W2.append(w + upd); total += np.abs(upd).sum()
+    return W2, b2, total / n_vars
+
+
+def sample_trajectories(real_env, policy, exploration, batch_size, max_timestep, rng, logger=None,
+                        diff_weights=None):
+    """env_helpers.py:352-460.  Per episode the policy's mean network is perturbed in parameter
+    space (prepare_policy; the reference saves / restores a checkpoint around it, here the episode
+    simply runs on a perturbed copy); per step get_action (env_helpers.py:37-48) adds
+    action_noise * randn(1) -- ONE scalar draw broadcast over all action dimensions, because the
+    reference takes `len(action)` of a [1, A] array -- and clips to the action bounds.
+    Returns (Os, As, Rs, info)."""
     import torch
     Os, As, Rs = [], [], []
     counter = 1
     with torch.no_grad():
-        W = [w.cpu().numpy().astype(np.float64) for w in policy.W]
-        b = [v.cpu().numpy().astype(np.float64) for v in policy.b]
-    n = len(W)
+        W0 = [w.cpu().numpy().astype(np.float64) for w in policy.W]
+        b0 = [v.cpu().numpy().astype(np.float64) for v in policy.b]
+    n = len(W0)
 
-    def mean_action(o):
+    def mean_action(o, W, b):
         h = o
         for i in range(n):
             h = h @ W[i] + b[i]
@@ -194,11 +223,15 @@ def sample_trajectories(real_env, policy, exploration, batch_size, max_timestep,
                 h = np.tanh(h)
         return h
 
+    changes = []
     while counter <= batch_size:
         o, a, r = [real_env.reset()], [], []
+        W, b, change = prepare_policy(W0, b0, exploration.get("param_noise", 0.0), diff_weights,
+                                      exploration.get("initial_param_std", 0.0), rng)
+        changes.append(change)
         for t in range(max_timestep):
             noise = exploration["action_noise"] * (rng.uniform() if exploration.get("vary_trajectory_noise") else 1.0)
-            act = np.clip(mean_action(o[-1]) + noise * rng.normal(size=real_env.A), -1.0, 1.0)   # get_action
+            act = np.clip(mean_action(o[-1], W, b) + noise * rng.randn(1), -1.0, 1.0)   # get_action
             obs, rew, done, _ = real_env.step(act)
             o.append(obs); a.append(act); r.append(rew)
             counter += 1
@@ -206,18 +239,19 @@ def sample_trajectories(real_env, policy, exploration, batch_size, max_timestep,
                 break
         Os.append(o); As.append(a); Rs.append(r)
     info = dict(EpisodesCollected=len(Os), TimeStepsCollected=counter - 1,
-                avg_eps_reward=float(np.mean([np.sum(x) for x in Rs])))
+                avg_eps_reward=float(np.mean([np.sum(x) for x in Rs])),
+                avg_weight_change=float(np.mean(changes)))
     return Os, As, Rs, info
 
 
 def collect_data(real_env, policy, sample_size, dynamics_data, dynamics_validation, input_rms, output_rms,
-                 rollout_params, rng, logger=None):
+                 rollout_params, rng, logger=None, diff_weights=None):
     """model_based_rl.py:758-857 (use_same_dataset / trajectory split)."""
     from .dynamics import add_rollout_data
     if sample_size == 0:
         return {}
     Os, As, Rs, info = sample_trajectories(real_env, policy, rollout_params["exploration"], sample_size,
-                                           rollout_params["max_timestep"], rng, logger)
+                                           rollout_params["max_timestep"], rng, logger, diff_weights)
     x_all, y_all = [], []
     for o, a in zip(Os, As):
         for t in range(len(o) - 1):
@@ -262,7 +296,7 @@ def train_models(real_env, nn_env, algo, fit, params, snapshot_dir=None, seed=0,
         reinit_every = int(dop["reinitialize"])
         reinitialize = (count == 1) or not (reinit_every <= 0 or count % reinit_every != 1)   # :550-556
         info = collect_data(real_env, policy, params["sample_size"], dynamics_data, dynamics_validation,
-                            input_rms, diff_rms, rp, rng, logger)
+                            input_rms, diff_rms, rp, rng, logger, diff_weights)   # :573-588
         t1 = time.time()
         norm = dict(in_mean=input_rms.mean, in_std=input_rms.std, diff_mean=diff_rms.mean, diff_std=diff_rms.std)
         fit.set_normalization(**norm)

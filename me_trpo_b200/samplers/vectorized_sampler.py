@@ -54,7 +54,10 @@ class VectorizedSampler(BaseSampler):
         rounds = -(-int(algo.batch_size) // per_round)
         return rounds * algo.max_path_length
 
-    def obtain_samples_flat(self, itr, determ=False, n_steps=None):
+    def obtain_samples_flat(self, itr, determ=False, n_steps=None, check=True):
+        """Time-major device buffers of one batch.  `check` waits for the kernel and raises if it
+        aborted on an internal wait timeout (the buffers would be partially written); pass False
+        only if the caller checks `self.rollout.synchronize()` itself before consuming them."""
         algo, env, pol = self.algo, self.algo.env, self.algo.policy
         B = self._n_envs
         T = int(n_steps or self._steps_for_batch())
@@ -66,6 +69,8 @@ class VectorizedSampler(BaseSampler):
         out = self.rollout.run(T, init, pool, seed=self.seed, offset=self._calls * (1 << 20),
                                determ=determ)
         self._calls += 1
+        if check:
+            self.rollout.synchronize()
         return out
 
     def obtain_samples(self, itr, determ=False):

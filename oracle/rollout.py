@@ -79,13 +79,15 @@ def _box_muller(xa, xb):
 
 
 def philox_normal(seed, step, rows, n, stream_base):
-    """[len(rows), n] N(0,1) fp32 for global step index `step` (uint32) and global row ids."""
+    """[len(rows), n] N(0,1) fp32 for the 64-bit global step index `step` and global row ids
+    (c0 = low word of the step, c3 = 'METR' ^ high word; csrc/philox.cuh)."""
     rows = np.asarray(rows, dtype=np.uint32)
     out = np.empty((len(rows), n), np.float32)
     k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+    step = int(step)
     for blk in range((n + 3) // 4):
-        x0, x1, x2, x3 = philox4x32(np.uint32(step), rows, np.uint32(stream_base + blk),
-                                    np.uint32(PHILOX_C3), k0, k1)
+        x0, x1, x2, x3 = philox4x32(np.uint32(step & 0xFFFFFFFF), rows, np.uint32(stream_base + blk),
+                                    np.uint32(PHILOX_C3 ^ ((step >> 32) & 0xFFFFFFFF)), k0, k1)
         n0, n1 = _box_muller(x0, x1)
         n2, n3 = _box_muller(x2, x3)
         for j, v in enumerate((n0, n1, n2, n3)):
@@ -95,11 +97,16 @@ def philox_normal(seed, step, rows, n, stream_base):
 
 
 def philox_index(seed, counter, rows, K, stream):
-    """[len(rows)] int32 in [0, K): mulhi(x0, K)."""
+    """[len(rows)] int32 in [0, K): mulhi(x0, K).  `counter`: 64-bit scalar step or a uint32 array
+    of per-row episode numbers."""
     rows = np.asarray(rows, dtype=np.uint32)
     k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
-    x0, _, _, _ = philox4x32(np.asarray(counter, dtype=np.uint32), rows, np.uint32(stream),
-                             np.uint32(PHILOX_C3), k0, k1)
+    if np.ndim(counter) == 0:
+        c = int(counter)
+        lo, hi = np.uint32(c & 0xFFFFFFFF), (c >> 32) & 0xFFFFFFFF
+    else:
+        lo, hi = np.asarray(counter, dtype=np.uint32), 0
+    x0, _, _, _ = philox4x32(lo, rows, np.uint32(stream), np.uint32(PHILOX_C3 ^ hi), k0, k1)
     return ((x0.astype(np.uint64) * np.uint64(K)) >> np.uint64(32)).astype(np.int32)
 
 
@@ -130,17 +137,16 @@ class PhiloxNoise:
         return np.arange(self.row0, self.row0 + B, dtype=np.uint32)
 
     def get_eps(self, t, B, A):
-        return philox_normal(self.seed, (self.offset + t) & 0xFFFFFFFF, self._rows(B), A, STREAM_EPS)
+        return philox_normal(self.seed, self.offset + t, self._rows(B), A, STREAM_EPS)
 
     def get_model_idx(self, t, B, K, episode):
         if self.sam_mode == "eps_rand":
             return philox_index(self.seed, episode.astype(np.uint32), self._rows(B), K,
                                 STREAM_EIDX).astype(np.int64)
-        return philox_index(self.seed, np.uint32((self.offset + t) & 0xFFFFFFFF), self._rows(B), K,
-                            STREAM_IDX).astype(np.int64)
+        return philox_index(self.seed, self.offset + t, self._rows(B), K, STREAM_IDX).astype(np.int64)
 
     def get_std_noise(self, t, B, S):
-        return philox_normal(self.seed, (self.offset + t) & 0xFFFFFFFF, self._rows(B), S, STREAM_STD)
+        return philox_normal(self.seed, self.offset + t, self._rows(B), S, STREAM_STD)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -436,6 +436,7 @@ def gen_vec_env():
                 obs0 = vec.reset()
                 k = "D_vec__%s__%s__" % (env_name, sam_mode)
                 put(k + "actions", acts)
+                put_norm(k, w)
                 put(k + "obs0", obs0)
                 put(k + "cfg", np.array([K, B, T, mpl, seed]))
                 states, rewards, dones, idx_used, std_noise, n_resets = [], [], [], [], [], []
@@ -497,6 +498,7 @@ def gen_trpo_iteration():
         k = "E_iter__%s__" % env_name
         put(k + "cfg", np.array([K, batch_size, T, n_iters, seed]))
         put(k + "discount", 0.97)
+        put_norm(k, w)
         rec = RecordingRandom()
         ref_env_helpers.np = NumpyProxy(rec)
         sampler_mod = sys.modules["samplers.vectorized_sampler"]
@@ -580,6 +582,7 @@ def gen_model_costs():
         init = ant_pool(rs, B, w.S) if env_name == "ant" else RI.states(seed + 11, B, w.S)
         k = "F_costs__%s__" % env_name
         put(k + "cfg", np.array([K, B, T, seed])); put(k + "gamma", gamma)
+        put_norm(k, w)
         put(k + "init", init)
         with np.errstate(invalid="ignore"):
             put(k + "policy_costs", w.sess.run(costs, {policy_training_init: init}))
@@ -643,6 +646,11 @@ def gen_data_collection():
     t = rs.randn(6, 12).astype(np.float32)
     put("G_ith__t", t)
     put("G_ith__out", np.stack([ref_utils.get_ith_tensor(t, i, 4) for i in range(3)]))
+
+
+def put_norm(k, w):
+    for nm, v in zip(["in_mean", "in_std", "diff_mean", "diff_std"], w.rms):
+        put(k + nm, v)
 
 
 def main():

@@ -133,3 +133,40 @@ def test_row_sharded_rollout_equals_unsharded_gloo(tmp_path):
     ref = orl.rollout_flat(env, inp["pol"], inp["models"], inp["norm"], inp["init"], inp["pool"],
                            orl.PhiloxNoise(1234, 7, 0, sam_mode), T, T_max)
     np.testing.assert_array_equal(got, ref["obs"])
+
+
+def test_sample_trajectories_param_noise_and_scalar_action_noise():
+    """env_helpers.py:37-59,352-460: per-episode parameter-space perturbation
+    param_noise * diff_weights * randn (biases then matrices; restored after the episode) and ONE
+    scalar action-noise draw per step broadcast over the action dimensions."""
+    torch = pytest.importorskip("torch")
+    from me_trpo_b200.model_based_rl import prepare_policy, sample_trajectories
+    from me_trpo_b200.policies import GaussianMLPPolicy
+    from me_trpo_b200.real_env import SyntheticEnv
+    pol = GaussianMLPPolicy(10, 2, (32, 32), device="cpu", seed=1)
+    W = [w.numpy().astype(np.float64) for w in pol.W]
+    b = [v.numpy().astype(np.float64) for v in pol.b]
+    n_wb = sum(w.size for w in W) + sum(v.size for v in b)
+    diff = np.full(n_wb + 2, 0.01)
+    # no diff_weights yet (first sweep): nothing is perturbed, initial_param_std must be 0
+    W1, b1, ch = prepare_policy(W, b, 3.0, None, 0.0, np.random.RandomState(0))
+    assert ch == 0.0 and W1 is W
+    with pytest.raises(AssertionError):
+        prepare_policy(W, b, 3.0, None, 0.5, np.random.RandomState(0))
+    # the reference's draw order: randn(n) over [b0, b1, b2, W0, W1, W2]
+    W2, b2, ch = prepare_policy(W, b, 3.0, diff, 0.0, np.random.RandomState(0))
+    z = np.random.RandomState(0).randn(n_wb)
+    np.testing.assert_allclose(b2[0] - b[0], 3.0 * 0.01 * z[:32])
+    o = sum(v.size for v in b)
+    np.testing.assert_allclose(W2[0] - W[0], (3.0 * 0.01 * z[o:o + W[0].size]).reshape(W[0].shape))
+    assert ch == pytest.approx(np.mean(np.abs(3.0 * 0.01 * z)))
+    assert np.array_equal(W[0], pol.W[0].numpy().astype(np.float64))     # originals untouched
+    # scalar action noise: with zero weights the action is noise * randn(1) in every dimension
+    for w in pol.W:
+        w.zero_()
+    env = SyntheticEnv("swimmer", seed=0)
+    expl = dict(action_noise=0.3, vary_trajectory_noise=False, param_noise=0.0, initial_param_std=0.0)
+    Os, As, Rs, info = sample_trajectories(env, pol, expl, 20, 10, np.random.RandomState(3))
+    acts = np.concatenate([np.asarray(a) for a in As])
+    assert acts.shape[1] == 2 and np.array_equal(acts[:, 0], acts[:, 1]) and np.abs(acts).max() > 0
+    assert info["TimeStepsCollected"] >= 20 and info["avg_weight_change"] == 0.0

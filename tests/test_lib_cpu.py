@@ -11,7 +11,7 @@ def test_library_exports_every_declared_symbol(metrpo_lib):
     syms = metrpo_lib.check_exports()
     for s in ["metrpo_rollout_create", "metrpo_rollout_run", "metrpo_rollout_step", "metrpo_rollout_reset",
               "metrpo_rollout_set_dynamics", "metrpo_rollout_set_policy", "metrpo_rollout_set_normalization",
-              "metrpo_rollout_destroy", "metrpo_last_error", "metrpo_version", "metrpo_selftest_umma"]:
+              "metrpo_rollout_destroy", "metrpo_last_error", "metrpo_version"]:
         assert s in syms
     assert b"sm_100a" in metrpo_lib.load().metrpo_version()
 

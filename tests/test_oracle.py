@@ -37,6 +37,21 @@ def test_philox_normal_moments_and_index_range():
     assert np.all(np.abs(np.bincount(idx) / 20000.0 - 0.2) < 0.02)
 
 
+def test_philox_step_counter_is_64_bit():
+    """Offsets that differ by 2**32 must not replay the stream (VectorizedSampler spaces its calls
+    by 2**20 steps for the whole run: call n and call n + 4096 used to collide)."""
+    rows = np.arange(64)
+    a = orl.philox_normal(7, 5, rows, 6, orl.STREAM_EPS)
+    b = orl.philox_normal(7, 5 + (1 << 32), rows, 6, orl.STREAM_EPS)
+    assert not np.array_equal(a, b) and abs(np.corrcoef(a.ravel(), b.ravel())[0, 1]) < 0.2
+    ia = orl.philox_index(7, 5, rows, 5, orl.STREAM_IDX)
+    ib = orl.philox_index(7, 5 + (1 << 32), rows, 5, orl.STREAM_IDX)
+    assert not np.array_equal(ia, ib)
+    n1 = orl.PhiloxNoise(7, offset=(1 << 32) - 2)       # the carry into the high word
+    np.testing.assert_array_equal(n1.get_eps(2, 64, 6), orl.philox_normal(7, 1 << 32, rows, 6, orl.STREAM_EPS))
+    np.testing.assert_array_equal(n1.get_eps(1, 64, 6), orl.philox_normal(7, (1 << 32) - 1, rows, 6, orl.STREAM_EPS))
+
+
 @pytest.mark.parametrize("case", mg.CASES, ids=[c[0] for c in mg.CASES])
 @pytest.mark.parametrize("mma", ["fp32", "bf16"])
 def test_oracle_matches_golden(case, mma):

@@ -94,6 +94,24 @@ def test_rollout_matches_oracle_larger_cases(case):
     assert np.isfinite(dev["obs"]).all()
 
 
+def test_philox_offsets_beyond_32_bits():
+    """The step counter of the noise streams is 64 bits wide: offsets 2**32 apart give different
+    noise, the carry into the high word is handled, and the kernel still matches the oracle."""
+    case = [c for c in mg.CASES if c[8] == "philox" and c[7] == "step_rand"][0]
+    name, env, K, B, T, T_max, hidden, sam_mode, _ = case
+    lo, inp = _device_run(case, offset=5)
+    hi, _ = _device_run(case, inp=inp, offset=5 + (1 << 32))
+    assert not np.array_equal(lo["act"], hi["act"])
+    off = (1 << 32) - 2                                   # steps 2.. run with the high word = 1
+    dev, _ = _device_run(case, inp=inp, offset=off)
+    noise = orl.PhiloxNoise(1234, off, 0, sam_mode)
+    ref = orl.rollout_flat(env, inp["pol"], inp["models"], inp["norm"], inp["init"], inp["pool"], noise, T,
+                           T_max, sam_mode=sam_mode, mma="bf16")
+    for k in ("obs", "act", "rew"):
+        assert np.max(np.abs(dev[k] - ref[k])) <= TOL_BF16, k
+    assert np.array_equal(dev["done"], ref["done"])
+
+
 def test_determ_mode_actions_equal_mean():
     case = mg.CASES[0]
     dev, inp = _device_run(case, determ=True)

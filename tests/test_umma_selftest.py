@@ -18,14 +18,14 @@ CASES = [
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode,N,K", CASES)
 def test_umma_layouts(metrpo_lib, mode, N, K):
-    lib = metrpo_lib.load()
+    lib = metrpo_lib.load_dev()
     g = torch.Generator(device="cpu").manual_seed(1000 * mode + N + K)
     A = torch.randn(128, K, generator=g).to(torch.bfloat16).cuda()
     B = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
     C = torch.full((128, N), float("nan"), device="cuda", dtype=torch.float32)
     st = lib.metrpo_selftest_umma(mode, N, K, 1, metrpo_lib.ptr(A), metrpo_lib.ptr(B),
                                   metrpo_lib.ptr(C), None, metrpo_lib.stream_ptr())
-    metrpo_lib.check(st, "selftest")
+    metrpo_lib.check_dev(st, "selftest")
     torch.cuda.synchronize()
     ref = A.float() @ B.float().t()
     err = (C - ref).abs().max().item()
@@ -35,7 +35,7 @@ def test_umma_layouts(metrpo_lib, mode, N, K):
 
 @pytest.mark.gpu
 def test_umma_selftest_rejects_bad_shapes(metrpo_lib):
-    lib = metrpo_lib.load()
+    lib = metrpo_lib.load_dev()
     st = lib.metrpo_selftest_umma(0, 24, 64, 1, None, None, None, None, None)
     assert st == -1
-    assert "N" in metrpo_lib.last_error()
+    assert b"N" in lib.metrpo_last_error()

@@ -4,11 +4,11 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from me_trpo_b200 import lib as L
-lib = L.load()
+lib = L.load_dev()
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 res = []
 def run(ts, N, two, a_col, d_col, wait_each, reps=512):
-    L.check(lib.metrpo_bench_mma(ts, N, reps, two, a_col, d_col, wait_each, L.ptr(out), None), "bench")
+    L.check_dev(lib.metrpo_bench_mma(ts, N, reps, two, a_col, d_col, wait_each, L.ptr(out), None), "bench")
     torch.cuda.synchronize()
     a, b = out.tolist()
     r = dict(ts=ts, N=N, sync=wait_each, issue_cyc_per_4mma=a / reps, total_cyc_per_4mma=b / reps)

@@ -4,13 +4,13 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from me_trpo_b200 import lib as L
-lib = L.load()
+lib = L.load_dev()
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
 res = []
 for kind, name, macs in ((0, "m16n8k8.tf32", 1024), (1, "m16n8k16.bf16", 2048)):
     for warps in (1, 4, 8, 16):
         reps = 2000
-        L.check(lib.metrpo_bench_mma_sync(kind, warps, reps, L.ptr(out), None), "bench")
+        L.check_dev(lib.metrpo_bench_mma_sync(kind, warps, reps, L.ptr(out), None), "bench")
         torch.cuda.synchronize()
         cyc = out.tolist()[0]
         n = reps * 8 * warps

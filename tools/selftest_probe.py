@@ -3,7 +3,7 @@ tensor-pipe cycle counts.  Usage on the GPU box: python tools/selftest_probe.py"
 import ctypes, os, sys, json
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = ctypes.CDLL(os.path.join(ROOT, "me_trpo_b200", "libmetrpo.so"))
+lib = ctypes.CDLL(os.path.join(ROOT, "me_trpo_b200", "libmetrpo_dev.so"))
 lib.metrpo_last_error.restype = ctypes.c_char_p
 vp = ctypes.c_void_p
 lib.metrpo_selftest_umma.argtypes = [ctypes.c_int] * 4 + [vp] * 5
