@@ -19,13 +19,58 @@ import sys
 import threading
 import time
 
-import numpy as np
+
+def _cpu_threads_env():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; NumPy's BLAS reads the
+    variable when it is first imported.  The CPU legs of this file (--impl reference, and the
+    cpu_baseline of the CUDA arm at N = 1) must see all host cores, so the variables are set
+    explicitly BEFORE numpy is imported; the thread count actually used is read back through
+    threadpoolctl and reported in the JSON line."""
+    want_all = "reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1
+    if want_all:
+        n = str(os.cpu_count() or 1)
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = n
+
+
+_cpu_threads_env()
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# BASELINE.json configs: name -> (env, K, total rows, horizon, hidden, GPUs the config names)
+WORKLOADS = {
+    "swimmer": ("swimmer", 5, 100, 200, 512, 1),           # configs[0]: the reference's own JSON shape
+    "half-cheetah": ("half-cheetah", 5, 4096, 1000, 1024, 1),     # configs[1]  (the headline metric)
+    "hopper": ("hopper", 10, 4096, 1000, 1024, 1),                # configs[2]
+    "ant": ("ant", 20, 16384, 1000, 1024, 4),                     # configs[3]
+    "humanoid": ("humanoid", 20, 65536, 1000, 1024, 8),           # configs[4]
+}
 ENV, K_MODELS, B_ROWS, HORIZON, HIDDEN = "half-cheetah", 5, 4096, 1000, 1024
 E2E_CHUNKS = int(os.environ.get("METRPO_E2E_CHUNKS", "8"))
+
+
+def select_workload(args, world):
+    """Sets the module-level shape from --config / --scaling.  weak (default): the per-GPU share of
+    the config is fixed (total rows / the GPU count the config names) and the job grows with N;
+    strong: the config's TOTAL rows are split over the N ranks."""
+    global ENV, K_MODELS, B_ROWS, HORIZON, HIDDEN
+    env, K, rows, T, hidden, gpus = WORKLOADS[args.config]
+    per_gpu = rows // gpus if args.scaling == "weak" else -(-rows // world)
+    ENV, K_MODELS, B_ROWS, HORIZON, HIDDEN = env, K, per_gpu, T, hidden
+    return workload_config(args, world)
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line -- identical for both arms (--impl cuda / reference)."""
+    env, K, rows, T, hidden, gpus = WORKLOADS[args.config]
+    total = B_ROWS * world
+    return {"workload": "%s K=%d B=%d/GPU horizon=%d step_rand (BASELINE configs[%d])"
+                        % (env, K, B_ROWS, T, list(WORKLOADS).index(args.config)),
+            "hidden": hidden, "rows_per_gpu": B_ROWS, "rows_total": total, "noise": "philox",
+            "l2": "512 MiB flush between timed iterations; weights (bf16) are re-streamed from L2 by design "
+                  "inside each launch", "parallelism": "rows sharded, no collective"}
 METRIC = "simulated env steps/sec (ensemble x batch x horizon)"
 UNIT = "units/s"
 
@@ -89,27 +134,46 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_reference_rate(steps_sample, blas_threads=None, seed=0):
+def blas_info():
+    try:
+        from threadpoolctl import threadpool_info
+        return [{"lib": i.get("internal_api"), "threads": i.get("num_threads")} for i in threadpool_info()]
+    except Exception:
+        return []
+
+
+def cpu_reference_rate(steps_sample, threads=None, seed=0, rows=None, horizon=None):
     """Times the reference path's CPU restatement (oracle/, reference-faithful structure:
     per-step Python loop, all-K fp32 NumPy forward, per-env bookkeeping) on `steps_sample` steps of
-    the same workload.  Returns (units/s, seconds, cores used)."""
+    the workload (optionally with `rows` parallel envs instead of the workload's).  `threads`
+    limits the BLAS pool (None = all host cores).  Returns (units/s, seconds, BLAS threads used)."""
     from oracle import rollout as orl
-    spec, models, pol, norm, init, pool = make_problem(seed)
+    from threadpoolctl import threadpool_limits
+    B = int(rows or B_ROWS)
+    T = int(horizon or HORIZON)
+    spec, models, pol, norm, init, pool = make_problem(seed, B)
     noise = orl.PhiloxNoise(1, 0, 0, "step_rand")
-    ve = orl.VecSimpleEnvOracle(ENV, models, norm, B_ROWS, HORIZON, "step_rand", noise, pool,
+    ve = orl.VecSimpleEnvOracle(ENV, models, norm, B, T, "step_rand", noise, pool,
                                 spec["S"], spec["A"], spec["drop"], np.float32, "fp32")
-    t0 = time.perf_counter()
-    orl.obtain_samples(ve, pol, init, batch_size=B_ROWS * HORIZON, max_steps=steps_sample)
-    dt = time.perf_counter() - t0
-    return K_MODELS * B_ROWS * steps_sample / dt, dt, os.cpu_count()
+    n_threads = int(threads or os.cpu_count() or 1)
+    with threadpool_limits(limits=n_threads):
+        t0 = time.perf_counter()
+        orl.obtain_samples(ve, pol, init, batch_size=B * T, max_steps=steps_sample)
+        dt = time.perf_counter() - t0
+    used = max([i["threads"] or 1 for i in blas_info()] + [1])
+    return K_MODELS * B * steps_sample / dt, dt, min(n_threads, used)
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU path (restated in oracle/, since TF1.4 + rllab +
-    MuJoCo cannot run here) on the host cores of the box, all BLAS threads."""
+    """--impl reference: the reference's own CPU path (restated in oracle/ and pinned to the
+    reference's code by tests/test_ref_fixtures.py; TF1.4 + rllab + MuJoCo cannot run here) on the
+    host cores of the box.  Headline value: all BLAS threads, BASELINE shape.  Also reported: one
+    BLAS thread (the reference pins TF to 1 thread, utils.py:229-232) and the reference's own
+    sampler shape (100 parallel envs, samplers/vectorized_sampler.py:26-27)."""
     if rank != 0:
         return
-    sample = 10  # env-steps of 5 x 4096 rows per bench step (bounded sample; steps are homogeneous)
+    config = select_workload(args, world)
+    sample = 10 if B_ROWS >= 1024 else 100   # env-steps per bench step (bounded sample; steps are homogeneous)
     rates = []
     for i in range(args.warmup + args.steps):
         r, dt, cores = cpu_reference_rate(sample, seed=i)
@@ -117,15 +181,23 @@ def run_reference(args, rank, world):
             rates.append((r, dt))
     value = float(np.mean([r for r, _ in rates]))
     ms = float(np.mean([dt for _, dt in rates]) * 1e3)
+    r1, dt1, _ = cpu_reference_rate(max(1, sample // 5), threads=1)
+    r100, dt100, _ = cpu_reference_rate(100, rows=100)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "half-cheetah K=5 B=4096 horizon=1000 step_rand (BASELINE configs[1])",
-                   "sample_env_steps_per_bench_step": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                         "sample": "%d env-steps x 5 models x 4096 rows per bench step, NumPy fp32 with all "
-                                   "BLAS threads, reference-faithful Python loop (oracle/rollout.py)" % sample},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "host_cores": os.cpu_count(), "blas": blas_info(),
+                         "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
+                         "sample": "%d env-steps x %d models x %d rows per bench step (ms_per_step is for this "
+                                   "sample, not a %d-step horizon), NumPy fp32, reference-faithful Python loop "
+                                   "(oracle/rollout.py)" % (sample, K_MODELS, B_ROWS, HORIZON),
+                         "one_thread": {"value": r1, "unit": UNIT, "cores": 1, "seconds": dt1,
+                                        "why": "the reference pins TF to 1 intra/inter-op thread (utils.py:229-232)"},
+                         "reference_sampler_shape": {"value": r100, "unit": UNIT, "rows": 100, "seconds": dt100,
+                                                     "why": "n_envs is capped at 100 (samplers/vectorized_sampler.py:26-27)"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -144,9 +216,10 @@ def run_cuda(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
+    config = select_workload(args, world)
     spec, models, pol, norm, init, pool = make_problem(0)
     T = HORIZON
-    row_offset = rank * B_ROWS                         # weak scaling: 4096 rows per GPU
+    row_offset = rank * B_ROWS                         # rows sharded by rank, global-row noise keys
     ro = EnsembleRollout(ENV, K_MODELS, B_ROWS, T, hidden=HIDDEN, device=dev, row_offset=row_offset)
     ro.set_dynamics_ensemble(models)
     ro.set_normalization(**norm)
@@ -257,26 +330,31 @@ def run_cuda(args, rank, local_rank, world):
         peak_src = "MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS bf16)" if peaks else "fallback 1.59 PFLOP/s"
         kernel_ms = float(np.mean(per_step))            # the step IS one launch of the persistent kernel
         achieved_tf = flops_per_step(spec, K_MODELS, B_ROWS, T, HIDDEN) / (kernel_ms * 1e-3) / 1e12
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_rollout_ncu_summary.json")))["dram_bytes_per_launch_T1000_est"]
-        except Exception:
-            pass
-        cpu_rate, cpu_dt, cores = cpu_reference_rate(40)
+        traffic, traffic_src = None, None
+        if args.config == "half-cheetah":
+            for name in ("r2_rollout_ncu_summary.json", "r1_rollout_ncu_summary.json"):
+                try:
+                    traffic = json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch_T1000_est"]
+                    traffic_src = "profiles/%s (ncu --set full capture of this kernel and shape; not re-measured in this run)" % name
+                    break
+                except Exception:
+                    pass
+        cpu = None
+        if world == 1:            # the contract: rank 0 at N = 1 only
+            cpu_rate, cpu_dt, cores = cpu_reference_rate(40 if B_ROWS >= 1024 else 200)
+            cpu = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port", "host_cores": os.cpu_count(),
+                   "blas": blas_info(),
+                   "sample": "%d of %d env-steps of the same workload (homogeneous steps), NumPy fp32, %d BLAS "
+                             "threads, reference-faithful loop; %.1f s" % (40 if B_ROWS >= 1024 else 200, T, cores, cpu_dt)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "half-cheetah K=5 B=4096/GPU horizon=1000 step_rand (BASELINE configs[1])",
-                       "hidden": HIDDEN, "rows_per_gpu": B_ROWS, "noise": "philox on device",
-                       "l2": "512 MiB flush between timed iterations; weights (11 MB bf16) are re-streamed from L2 "
-                             "by design inside each launch", "parallelism": "rows sharded, no collective"},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": config,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "metrpo::rollout_kernel", "kernel_ms": kernel_ms},
-            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "40 of 1000 env-steps of the same workload (homogeneous steps), NumPy fp32, "
-                                       "all BLAS threads, reference-faithful loop; %.1f s" % cpu_dt},
+                         "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "kernel": "metrpo::rollout_kernel", "kernel_ms": kernel_ms},
+            "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "gpu_launches_per_step": E2E_CHUNKS,
                     "what": "pinned host init/reset states -> device, fused rollout in %d chained launches, whole "
@@ -297,6 +375,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--config", default="half-cheetah", choices=list(WORKLOADS),
+                    help="BASELINE.json config (default: configs[1], the one the metric is quoted on)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's per-GPU share on every rank; strong: its total rows split over N")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

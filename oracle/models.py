@@ -74,9 +74,25 @@ def default_norm(S, A):
                 diff_mean=np.zeros(S, np.float32), diff_std=np.full(S, 0.1, np.float32))
 
 
+_BF16_W_CACHE = {}
+
+
+def _bf16_weight(W):
+    """bf16-rounded float64 copy of a weight matrix, memoised per array object (the rollout calls
+    this K x T times with the same matrices; rounding 1 M elements each time dominated the run)."""
+    key = id(W)
+    hit = _BF16_W_CACHE.get(key)
+    if hit is None or hit[0] is not W:
+        if len(_BF16_W_CACHE) > 256:
+            _BF16_W_CACHE.clear()
+        hit = (W, bf16_round(W).astype(np.float64))
+        _BF16_W_CACHE[key] = hit
+    return hit[1]
+
+
 def _matmul(h, W, dtype, mma):
     if mma == "bf16":
-        return (bf16_round(h).astype(np.float64) @ bf16_round(W).astype(np.float64)).astype(np.float32)
+        return (bf16_round(h).astype(np.float64) @ _bf16_weight(W)).astype(np.float32)
     return h.astype(dtype) @ W.astype(dtype)
 
 

@@ -1,0 +1,188 @@
+"""Parity of the CUDA rollout on the shapes that are BENCHMARKED (BASELINE.json configs[1..4]) and
+the cost of bf16 tensor-core arithmetic relative to the reference's fp32 over long horizons.
+
+(a) the exact bench workloads -- synthetic.make_problem nets (what bench.py times), Philox noise on
+    device, full width H = 1024 and full K: kernel vs the oracle in the kernel's arithmetic
+    (bf16 operands, fp32 accumulate) <= 1e-4 and vs the reference's fp32 arithmetic <= 1e-3 over a
+    short open loop (the CPU oracle runs ~0.2 M units/s, so T is sized for a few seconds);
+(b) open-loop DRIFT of the bf16 kernel against the fp32 oracle at t in {1, 10, 100, 1000}, for the
+    bench nets (output layer x0.1) and for an unscaled contractive surrogate of a fitted model;
+    the table is written to gpurun_out/drift_table.json (copied to profiles/ when it changes);
+(c) what that drift does to the TRPO half: post-centring advantages and the mean KL after one
+    policy update, device rollout (bf16) vs fp32-oracle rollout on the same noise.
+Tolerances are asserted below and quoted in DESIGN.md section 3."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+from oracle import rollout as orl, trpo as otr  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL_BF16, TOL_FP32 = 1e-4, 1e-3
+
+
+def _device(env, K, B, T, T_max, hidden, models, pol, norm, init, pool, seed=1, offset=0, **kw):
+    from me_trpo_b200.rollout import EnsembleRollout
+    ro = EnsembleRollout(env, K, B, T_max, hidden=hidden, device="cuda:0")
+    ro.set_dynamics_ensemble(models)
+    ro.set_normalization(**norm)
+    ro.set_policy(pol["W"], pol["b"], pol["log_std"])
+    out = ro.run(T, init, pool, seed=seed, offset=offset, **kw)
+    ro.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    ro.close()
+    return res
+
+
+# (a) ---------------------------------------------------------------------------------------------
+BENCH_SHAPES = [   # env, K, rows per GPU, hidden, steps compared
+    ("half-cheetah", 5, 4096, 1024, 20),
+    ("hopper", 10, 4096, 1024, 10),
+    ("ant", 20, 4096, 1024, 5),
+    ("humanoid", 20, 8192, 1024, 3),
+]
+
+
+@pytest.mark.parametrize("env,K,B,hidden,T", BENCH_SHAPES, ids=[c[0] for c in BENCH_SHAPES])
+def test_bench_workload_matches_oracle(env, K, B, hidden, T):
+    from me_trpo_b200 import synthetic
+    spec, models, pol, norm, init, pool = synthetic.make_problem(env, K, B, hidden=hidden, seed=0)
+    if env == "ant":
+        init[:, 2] = 0.6
+        pool[:, 2] = 0.6
+    dev = _device(env, K, B, T, 1000, hidden, models, pol, norm, init, pool, seed=1, offset=0)
+    for mma, tol in (("bf16", TOL_BF16), ("fp32", TOL_FP32)):
+        noise = orl.PhiloxNoise(1, 0, 0, "step_rand")
+        with np.errstate(invalid="ignore"):
+            ref = orl.rollout_flat(env, pol, models, norm, init, pool, noise, T, 1000, "step_rand", mma=mma)
+        errs = {k: float(np.max(np.abs(dev[k] - ref[k]))) for k in ("obs", "act", "mean", "rew", "final_states")}
+        print("bench shape %s K=%d B=%d H=%d T=%d vs %s oracle: %s" % (env, K, B, hidden, T, mma, errs))
+        assert all(e <= tol for e in errs.values()), (env, mma, errs)
+        assert np.array_equal(dev["done"], ref["done"])
+
+
+# (b) ---------------------------------------------------------------------------------------------
+def contractive_models(rng, S, A, drop, hidden, K, pull=0.5, rand_scale=0.3):
+    """Unscaled (out_scale = 1) surrogate of a FITTED model: a random Xavier net of full output
+    scale whose last layer additionally reads a pass-through of the state (relu(z) - relu(-z) pairs
+    through both hidden layers) with gain -pull / sigma_delta, so that x' = x + sigma_delta * o
+    contracts toward the origin like a damped physical system instead of exploding."""
+    from oracle import models as om
+    din = S + A - drop
+    models = om.init_dynamics(rng, S, A, drop, hidden, K, out_scale=rand_scale)
+    for m in models:
+        for j in range(S - drop):           # state columns that survive the input column drop
+            zi = j                           # index in the network input
+            s_idx = j + drop                 # index in the state
+            for sign, unit in ((1.0, 2 * j), (-1.0, 2 * j + 1)):
+                m["W0"][:, unit] = 0; m["W0"][zi, unit] = sign; m["b0"][unit] = 0
+                m["W1"][:, unit] = 0; m["W1"][unit, :] *= 0; m["W1"][unit, unit] = 1.0; m["b1"][unit] = 0
+                m["W2"][unit, :] = 0; m["W2"][unit, s_idx] = -sign * pull / 0.1
+    return models
+
+
+DRIFT_T = (1, 10, 100, 1000)
+
+
+@pytest.mark.parametrize("kind", ["bench_nets_x0.1", "contractive_unscaled"])
+def test_open_loop_drift_vs_fp32_oracle(kind):
+    from me_trpo_b200 import synthetic
+    env, K, B, hidden, T = "half-cheetah", 5, 128, 1024, 1000
+    spec, models, pol, norm, init, pool = synthetic.make_problem(env, K, B, hidden=hidden, seed=0)
+    if kind == "contractive_unscaled":
+        models = contractive_models(np.random.RandomState(5), spec["S"], spec["A"], spec["drop"], hidden, K)
+    dev = _device(env, K, B, T, T, hidden, models, pol, norm, init, pool, seed=1)
+    rows = {}
+    refs = {}
+    for mma, Tm in (("fp32", T), ("bf16", 101)):      # the bf16 oracle is 5x slower: first 100 steps only
+        noise = orl.PhiloxNoise(1, 0, 0, "step_rand")
+        refs[mma] = orl.rollout_flat(env, pol, models, norm, init, pool, noise, Tm, T, "step_rand", mma=mma)
+    scale = float(np.abs(refs["fp32"]["obs"]).max())
+    for t in DRIFT_T:
+        nxt = lambda r: r["obs"][t] if t < len(r["obs"]) else r["final_states"]      # state after t steps
+        d32 = np.abs(nxt(dev) - nxt(refs["fp32"]))
+        rows[str(t)] = dict(max_vs_fp32=float(d32.max()), median_vs_fp32=float(np.median(d32)))
+        if t <= 100:
+            d16 = np.abs(nxt(dev) - nxt(refs["bf16"]))
+            rows[str(t)].update(max_vs_bf16_oracle=float(d16.max()), median_vs_bf16_oracle=float(np.median(d16)))
+    ret_dev, ret_ref = dev["rew"].sum(0), refs["fp32"]["rew"].sum(0)
+    table = dict(kind=kind, env=env, K=K, rows=B, hidden=hidden, horizon=T, state_scale=scale, drift=rows,
+                 return_mean_fp32=float(ret_ref.mean()), return_mean_dev=float(ret_dev.mean()),
+                 return_abs_err_max=float(np.abs(ret_dev - ret_ref).max()),
+                 return_abs_err_median=float(np.median(np.abs(ret_dev - ret_ref))))
+    print("drift %s: %s" % (kind, json.dumps(table)))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    path = os.path.join(ROOT, "gpurun_out", "drift_table.json")
+    old = json.load(open(path)) if os.path.exists(path) else {}
+    old[kind] = table
+    json.dump(old, open(path, "w"), indent=1)
+    assert np.isfinite(dev["obs"]).all() and np.isfinite(refs["fp32"]["obs"]).all()
+    # one step: bf16 operand rounding only
+    assert rows["1"]["max_vs_fp32"] <= 1e-3
+    # ten steps: still well inside the fp32 tolerance band of the short-horizon tests
+    assert rows["10"]["max_vs_fp32"] <= 5e-3 * max(1.0, scale)
+    # long horizon: the MEDIAN state error stays small relative to the state scale (a few rows may
+    # diverge through the discontinuous step_rand / ReLU structure; the max is reported, not asserted)
+    assert rows["1000"]["median_vs_fp32"] <= 5e-2 * max(1.0, scale)
+    # and the quantity TRPO consumes, the per-path return, moves by a small fraction of its spread
+    assert table["return_abs_err_median"] <= 0.05 * max(1.0, float(np.abs(ret_ref - ret_ref.mean()).mean()))
+
+
+# (c) ---------------------------------------------------------------------------------------------
+def test_advantages_and_kl_after_one_update_device_vs_fp32_rollout():
+    """Same policy, same noise: (device bf16 rollout -> device process -> device TRPO update)
+    against (fp32 oracle rollout -> float64 oracle process -> float64 oracle update)."""
+    from me_trpo_b200 import synthetic
+    from me_trpo_b200.trpo import PolicyUpdate
+    env, K, B, hidden, T = "half-cheetah", 5, 128, 1024, 100
+    spec, models, pol, norm, init, pool = synthetic.make_problem(env, K, B, hidden=hidden, seed=0)
+    pol["log_std"] = np.full(spec["A"], -0.5, np.float32)
+    S, A = spec["S"], spec["A"]
+    dev = _device(env, K, B, T, T, hidden, models, pol, norm, init, pool, seed=1)
+    noise = orl.PhiloxNoise(1, 0, 0, "step_rand")
+    ref = orl.rollout_flat(env, pol, models, norm, init, pool, noise, T, T, "step_rand", mma="fp32")
+    # oracle side
+    ref_paths = orl.paths_from_flat(ref, pol["log_std"])
+    data = otr.process_samples(ref_paths, otr.LinearFeatureBaselineOracle(), 1.0)
+    dims = [S, 32, 32, A]
+    tr = otr.TRPOOracle(dims)
+    theta0 = otr.flatten_params(pol)
+    inputs = (data["observations"], data["actions"], data["advantages"], data["agent_infos"]["mean"],
+              data["agent_infos"]["log_std"])
+    theta_ref, info_ref = tr.optimize(theta0, inputs)
+    # device side
+    pu = PolicyUpdate(dims, device="cuda:0")
+    d = {k: torch.tensor(v, device="cuda") for k, v in dev.items()}
+    pr = pu.process(d["obs"], d["rew"], d["done"], discount=1.0)
+    N = T * B
+    theta = torch.tensor(theta0.astype(np.float32), device="cuda")
+    ls = torch.tensor(pol["log_std"], device="cuda")
+    info = pu.update(theta, d["obs"].reshape(N, -1), d["act"].reshape(N, -1), pr["adv"].reshape(N),
+                     d["mean"].reshape(N, -1), ls, valid=pr["valid"].reshape(N)).cpu().numpy()
+    # advantages: oracle order is (finish step, row) with time inside a path = row-major over [row][t]
+    adv_dev = pr["adv"].cpu().numpy().T.reshape(-1)          # all paths end at T: path b = column b
+    adv_ref = np.asarray(data["advantages"])
+    adv_err = float(np.abs(adv_dev - adv_ref).max())
+    step_dev = theta.cpu().numpy().astype(np.float64) - theta0
+    step_ref = theta_ref - theta0
+    cos = float(step_dev @ step_ref / (np.linalg.norm(step_dev) * np.linalg.norm(step_ref) + 1e-30))
+    res = dict(adv_max_abs_err=adv_err, kl_dev=float(info[2]), kl_ref=float(info_ref["kl"]),
+               loss_after_dev=float(info[1]), loss_after_ref=float(info_ref["loss_after"]),
+               accepted_dev=bool(info[4] == 1.0), accepted_ref=bool(info_ref["accepted"]), step_cosine=cos,
+               T=T, rows=B)
+    print("post-update parity: %s" % json.dumps(res))
+    path = os.path.join(ROOT, "gpurun_out", "drift_table.json")
+    old = json.load(open(path)) if os.path.exists(path) else {}
+    old["trpo_after_one_update"] = res
+    json.dump(old, open(path, "w"), indent=1)
+    assert adv_err <= 5e-2                    # centred advantages have unit variance
+    assert res["accepted_dev"] and res["accepted_ref"]
+    assert abs(res["kl_dev"] - res["kl_ref"]) <= 2e-3 and res["kl_dev"] <= 0.01 + 1e-6
+    assert cos >= 0.98
+    pu.close()
