@@ -5,7 +5,7 @@ the cost of bf16 tensor-core arithmetic relative to the reference's fp32 over lo
     device, full width H = 1024 and full K: kernel vs the oracle in the kernel's arithmetic
     (bf16 operands, fp32 accumulate) <= 1e-4 and vs the reference's fp32 arithmetic <= 1e-3 over a
     short open loop (the CPU oracle runs ~0.2 M units/s, so T is sized for a few seconds);
-(b) open-loop DRIFT of the bf16 kernel against the fp32 oracle at t in {1, 10, 100, 1000}, for the
+(b) open-loop DRIFT of the bf16 kernel against the fp32 oracle at t in {1, 10, 100, 999}, for the
     bench nets (output layer x0.1) and for an unscaled contractive surrogate of a fitted model;
     the table is written to gpurun_out/drift_table.json (copied to profiles/ when it changes);
 (c) what that drift does to the TRPO half: post-centring advantages and the mean KL after one
@@ -87,7 +87,7 @@ def contractive_models(rng, S, A, drop, hidden, K, pull=0.5, rand_scale=0.3):
     return models
 
 
-DRIFT_T = (1, 10, 100, 1000)
+DRIFT_T = (1, 10, 100, 999)    # 999 = the pre-step state of the last step (at 1000 every row has been reset)
 
 
 @pytest.mark.parametrize("kind", ["bench_nets_x0.1", "contractive_unscaled"])
@@ -129,7 +129,7 @@ def test_open_loop_drift_vs_fp32_oracle(kind):
     assert rows["10"]["max_vs_fp32"] <= 5e-3 * max(1.0, scale)
     # long horizon: the MEDIAN state error stays small relative to the state scale (a few rows may
     # diverge through the discontinuous step_rand / ReLU structure; the max is reported, not asserted)
-    assert rows["1000"]["median_vs_fp32"] <= 5e-2 * max(1.0, scale)
+    assert rows["999"]["median_vs_fp32"] <= 5e-2 * max(1.0, scale)
     # and the quantity TRPO consumes, the per-path return, moves by a small fraction of its spread
     assert table["return_abs_err_median"] <= 0.05 * max(1.0, float(np.abs(ret_ref - ret_ref.mean()).mean()))
 
