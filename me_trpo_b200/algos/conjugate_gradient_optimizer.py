@@ -23,7 +23,15 @@ class ConjugateGradientOptimizer:
         self._max_constraint_val = None
         self._constraint_name = None
         self._kernels = None
+        self._dist_ctx = None
         self.last_info = None
+
+    def set_dist_ctx(self, ctx):
+        """Row-sharded samples: gradient, Fisher-vector products and (loss, kl) pairs are summed
+        over the ranks of `ctx` so that every rank takes the identical natural-gradient step."""
+        self._dist_ctx = ctx
+        if self._kernels is not None and ctx is not None and ctx.distributed:
+            self._kernels.enable_allreduce(ctx.group)
 
     def update_opt(self, loss, target, leq_constraint, inputs, extra_inputs=None,
                    constraint_name="constraint", *args, **kwargs):
@@ -36,6 +44,8 @@ class ConjugateGradientOptimizer:
         if self._kernels is not None:
             self._kernels.close()
         self._kernels = PolicyUpdate(dims, out_tanh=target.output_tanh, device=target.device)
+        if self._dist_ctx is not None and self._dist_ctx.distributed:
+            self._kernels.enable_allreduce(self._dist_ctx.group)
 
     # ------------------------------------------------------------------------------------------
     def _device_inputs(self, inputs):

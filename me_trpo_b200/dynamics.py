@@ -65,7 +65,7 @@ class EnsembleFit:
         for t, s in zip(ts, self._shapes()):
             if tuple(t.shape) != s:
                 raise ValueError("dynamics weight shape %s, expected %s" % (tuple(t.shape), s))
-        _lib.check(self._lib.metrpo_fit_set_weights(self._h, int(k), *[_lib.ptr(t) for t in ts], _lib.stream_ptr()),
+        _lib.check(self._lib.metrpo_fit_set_weights(self._h, int(k), *[_lib.ptr(t) for t in ts], _lib.stream_ptr(device=self.device)),
                    "fit_set_weights")
         self._keep = self._keep[-16:] + [ts]
 
@@ -76,7 +76,7 @@ class EnsembleFit:
 
     def get_weights(self, k):
         ts = [torch.empty(s, device=self.device) for s in self._shapes()]
-        _lib.check(self._lib.metrpo_fit_get_weights(self._h, int(k), *[_lib.ptr(t) for t in ts], _lib.stream_ptr()),
+        _lib.check(self._lib.metrpo_fit_get_weights(self._h, int(k), *[_lib.ptr(t) for t in ts], _lib.stream_ptr(device=self.device)),
                    "fit_get_weights")
         return dict(zip(self.WEIGHT_KEYS, ts))
 
@@ -86,12 +86,12 @@ class EnsembleFit:
     def set_normalization(self, in_mean, in_std, diff_mean, diff_std):
         ts = [_f32(t, self.device) for t in (in_mean, in_std, diff_mean, diff_std)]
         assert ts[0].numel() == self.S + self.A and ts[2].numel() == self.S
-        _lib.check(self._lib.metrpo_fit_set_normalization(self._h, *[_lib.ptr(t) for t in ts], _lib.stream_ptr()),
+        _lib.check(self._lib.metrpo_fit_set_normalization(self._h, *[_lib.ptr(t) for t in ts], _lib.stream_ptr(device=self.device)),
                    "fit_set_normalization")
         self._keep = self._keep[-16:] + [ts]
 
     def reset_adam(self):
-        _lib.check(self._lib.metrpo_fit_reset_adam(self._h, _lib.stream_ptr()), "fit_reset_adam")
+        _lib.check(self._lib.metrpo_fit_reset_adam(self._h, _lib.stream_ptr(device=self.device)), "fit_reset_adam")
 
     def step(self, x, y, batch, lr, idx=None, seed=0, offset=0, want_losses=True):
         """One Adam step of all K models.  x[n,S+A], y[n,S] device tensors; idx[batch*K] int32 sample
@@ -105,7 +105,7 @@ class EnsembleFit:
             assert ix.numel() == batch * self.K
         losses = torch.empty(self.K, device=self.device) if want_losses else None
         _lib.check(self._lib.metrpo_fit_step(self._h, _lib.ptr(x), _lib.ptr(y), n, _lib.ptr(ix), int(batch),
-                                             int(seed), int(offset), float(lr), _lib.ptr(losses), _lib.stream_ptr()),
+                                             int(seed), int(offset), float(lr), _lib.ptr(losses), _lib.stream_ptr(device=self.device)),
                    "fit_step")
         self._keep = self._keep[-16:] + [ix]
         return losses
@@ -117,11 +117,11 @@ class EnsembleFit:
         losses = torch.empty(self.K, device=self.device)
         improved = torch.empty(self.K, dtype=torch.uint8, device=self.device)
         _lib.check(self._lib.metrpo_fit_eval(self._h, _lib.ptr(x), _lib.ptr(y), int(x.shape[0]), int(snapshot),
-                                             _lib.ptr(losses), _lib.ptr(improved), _lib.stream_ptr()), "fit_eval")
+                                             _lib.ptr(losses), _lib.ptr(improved), _lib.stream_ptr(device=self.device)), "fit_eval")
         return losses, improved
 
     def restore_best(self):
-        _lib.check(self._lib.metrpo_fit_restore_best(self._h, _lib.stream_ptr()), "fit_restore_best")
+        _lib.check(self._lib.metrpo_fit_restore_best(self._h, _lib.stream_ptr(device=self.device)), "fit_restore_best")
 
     def last_launches(self):
         return int(self._lib.metrpo_fit_last_launches(self._h))

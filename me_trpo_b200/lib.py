@@ -195,7 +195,9 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def stream_ptr(stream=None):
+def stream_ptr(stream=None, device=None):
+    """Raw cudaStream_t of `stream`, or of the current stream of `device` (a handle's own device,
+    not whatever device happens to be current)."""
     import torch
-    s = stream if stream is not None else torch.cuda.current_stream()
+    s = stream if stream is not None else torch.cuda.current_stream(device)
     return ctypes.c_void_p(s.cuda_stream)

@@ -245,19 +245,30 @@ def sample_trajectories(real_env, policy, exploration, batch_size, max_timestep,
 
 
 def collect_data(real_env, policy, sample_size, dynamics_data, dynamics_validation, input_rms, output_rms,
-                 rollout_params, rng, logger=None, diff_weights=None):
-    """model_based_rl.py:758-857 (use_same_dataset / trajectory split)."""
+                 rollout_params, rng, logger=None, diff_weights=None, dist_ctx=None):
+    """model_based_rl.py:758-857 (use_same_dataset / trajectory split).  With several ranks only
+    rank 0 steps the real environment; the new transitions are broadcast."""
     from .dynamics import add_rollout_data
     if sample_size == 0:
         return {}
-    Os, As, Rs, info = sample_trajectories(real_env, policy, rollout_params["exploration"], sample_size,
-                                           rollout_params["max_timestep"], rng, logger, diff_weights)
-    x_all, y_all = [], []
-    for o, a in zip(Os, As):
-        for t in range(len(o) - 1):
-            x_all.append(np.concatenate([o[t], a[t]]))
-            y_all.append(o[t + 1])
-    x_all, y_all = np.asarray(x_all, np.float32), np.asarray(y_all, np.float32)
+    x_all = y_all = None
+    info = {}
+    if dist_ctx is None or dist_ctx.rank == 0:
+        Os, As, Rs, info = sample_trajectories(real_env, policy, rollout_params["exploration"], sample_size,
+                                               rollout_params["max_timestep"], rng, logger, diff_weights)
+        x_all, y_all = [], []
+        for o, a in zip(Os, As):
+            for t in range(len(o) - 1):
+                x_all.append(np.concatenate([o[t], a[t]]))
+                y_all.append(o[t + 1])
+        x_all, y_all = np.asarray(x_all, np.float32), np.asarray(y_all, np.float32)
+    if dist_ctx is not None and dist_ctx.distributed:
+        stats = np.asarray([info.get("EpisodesCollected", 0), info.get("TimeStepsCollected", 0),
+                            info.get("avg_eps_reward", 0.0), info.get("avg_weight_change", 0.0)], np.float64) \
+            if dist_ctx.rank == 0 else None
+        x_all, y_all, stats = dist_ctx.broadcast_arrays([x_all, y_all, stats], dynamics_data.device)
+        info = dict(EpisodesCollected=int(stats[0]), TimeStepsCollected=int(stats[1]),
+                    avg_eps_reward=float(stats[2]), avg_weight_change=float(stats[3]))
     assert len(x_all) >= sample_size
     add_rollout_data(x_all, y_all, dynamics_data, dynamics_validation, input_rms, output_rms,
                      rollout_params["split_ratio"])
@@ -265,7 +276,7 @@ def collect_data(real_env, policy, sample_size, dynamics_data, dynamics_validati
 
 
 def train_models(real_env, nn_env, algo, fit, params, snapshot_dir=None, seed=0, logger=None,
-                 sweep_iters=None, policy_validation_init=None):
+                 sweep_iters=None, policy_validation_init=None, dist_ctx=None):
     """The sweep loop of train_models (model_based_rl.py:546-755) for algo 'trpo': every sweep
     collects `sample_size` real transitions, refits the K dynamics models on the device
     (optimize_models), pushes the new weights + normalisers into the imaginary env, resets
@@ -276,6 +287,9 @@ def train_models(real_env, nn_env, algo, fit, params, snapshot_dir=None, seed=0,
     import time
     import torch
     from .dynamics import RunningMeanStd, data_collection, optimize_models
+    from .parallel import DistContext
+    ctx = dist_ctx if dist_ctx is not None else DistContext()
+    K_total = int(params["n_models"])
     logger = logger or logging.getLogger("me_trpo_b200")
     rng = np.random.RandomState(seed)
     rp, dop, pop_json = params["rollout_params"], params["dynamics_opt_params"], params["policy_opt_params"]
@@ -287,7 +301,9 @@ def train_models(real_env, nn_env, algo, fit, params, snapshot_dir=None, seed=0,
     input_rms = RunningMeanStd(shape=(fit.S + fit.A,), device=dev)
     diff_rms = RunningMeanStd(shape=(fit.S,), device=dev)
     if policy_validation_init is None:                                      # :444-487
-        policy_validation_init = np.asarray([real_env.reset() for _ in range(pop.batch_size)], np.float32)
+        policy_validation_init = (np.asarray([real_env.reset() for _ in range(pop.batch_size)], np.float32)
+                                  if ctx.rank == 0 else None)
+        (policy_validation_init,) = ctx.broadcast_arrays([policy_validation_init], dev)
     sweep_iters = int(sweep_iters or params["sweep_iters"])
     rows, start_time = [], time.time()
     diff_weights = None
@@ -296,17 +312,25 @@ def train_models(real_env, nn_env, algo, fit, params, snapshot_dir=None, seed=0,
         reinit_every = int(dop["reinitialize"])
         reinitialize = (count == 1) or not (reinit_every <= 0 or count % reinit_every != 1)   # :550-556
         info = collect_data(real_env, policy, params["sample_size"], dynamics_data, dynamics_validation,
-                            input_rms, diff_rms, rp, rng, logger, diff_weights)   # :573-588
+                            input_rms, diff_rms, rp, rng, logger, diff_weights, dist_ctx=ctx)   # :573-588
         t1 = time.time()
         norm = dict(in_mean=input_rms.mean, in_std=input_rms.std, diff_mean=diff_rms.mean, diff_std=diff_rms.std)
         fit.set_normalization(**norm)
         dlog = optimize_models(fit, dynamics_data, dynamics_validation, batch_size=min(dop["batch_size"], fit.max_rows),
                                learning_rate=dop["learning_rate"], log_every=dop["log_every"],
                                num_passes_threshold=dop["num_passes_threshold"], max_passes=dop["max_passes"],
-                               reinitialize=reinitialize, rng=None, seed=seed + count, logger=None)
+                               reinitialize=reinitialize, rng=None, seed=seed + count + 7919 * ctx.rank, logger=None)
         torch.cuda.synchronize()
         t2 = time.time()
-        nn_env.models = fit.get_ensemble()                                   # new weights -> imaginary env
+        # new weights -> imaginary env (with G ranks: every owner broadcasts the models it fitted)
+        nn_env.models = ctx.gather_models(fit.get_ensemble(), K_total)
+        if ctx.distributed:      # per-model diagnostics of the other ranks' models
+            stats = torch.tensor([float(dlog["n_updates"]), float(dlog["min_sum_validation_loss"])],
+                                 dtype=torch.float64, device=dev)
+            import torch.distributed as dist
+            mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=ctx.group)
+            dist.all_reduce(stats, group=ctx.group)
+            dlog["n_updates"], dlog["min_sum_validation_loss"] = int(mx[0].item()), float(stats[1].item())
         nn_env.norm = {k: v.clone() for k, v in norm.items()}
         if pop_json["trpo"].get("reset", False):                             # training.py:368-370
             policy.log_std.fill_(float(np.log(pop_json["trpo"]["init_std"])))

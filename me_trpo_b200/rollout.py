@@ -84,7 +84,7 @@ class EnsembleRollout:
             if tuple(t.shape) != s:
                 raise ValueError("dynamics weight shape %s, expected %s" % (tuple(t.shape), s))
         _lib.check(self._lib.metrpo_rollout_set_dynamics(self._h, int(k), *[_lib.ptr(t) for t in ts],
-                                                         _lib.stream_ptr()), "set_dynamics")
+                                                         _lib.stream_ptr(device=self.device)), "set_dynamics")
         self._keep.append(ts)
 
     def set_dynamics_ensemble(self, models):
@@ -96,7 +96,7 @@ class EnsembleRollout:
         ts = [_f32(t, self.device) for t in (in_mean, in_std, diff_mean, diff_std)]
         assert ts[0].numel() == self.S + self.A and ts[2].numel() == self.S
         _lib.check(self._lib.metrpo_rollout_set_normalization(self._h, *[_lib.ptr(t) for t in ts],
-                                                              _lib.stream_ptr()), "set_normalization")
+                                                              _lib.stream_ptr(device=self.device)), "set_normalization")
         self._keep.append(ts)
 
     def set_policy(self, Ws, bs, log_std):
@@ -107,7 +107,7 @@ class EnsembleRollout:
         ls = _f32(log_std, self.device)
         Wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in Ws])
         bp = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bs])
-        _lib.check(self._lib.metrpo_rollout_set_policy(self._h, Wp, bp, _lib.ptr(ls), _lib.stream_ptr()),
+        _lib.check(self._lib.metrpo_rollout_set_policy(self._h, Wp, bp, _lib.ptr(ls), _lib.stream_ptr(device=self.device)),
                    "set_policy")
         self._keep.append((Ws, bs, ls))
         self.log_std = ls
@@ -116,7 +116,7 @@ class EnsembleRollout:
     def reset(self, states):
         st = _f32(states, self.device)
         assert tuple(st.shape) == (self.B, self.S)
-        _lib.check(self._lib.metrpo_rollout_reset(self._h, _lib.ptr(st), _lib.stream_ptr()), "reset")
+        _lib.check(self._lib.metrpo_rollout_reset(self._h, _lib.ptr(st), _lib.stream_ptr(device=self.device)), "reset")
         self._keep.append(st)
 
     def step(self, actions, reset_states, model_idx=None, std_noise=None, seed=0, offset=0):
@@ -130,7 +130,7 @@ class EnsembleRollout:
         done = torch.empty(self.B, dtype=torch.uint8, device=dev)
         _lib.check(self._lib.metrpo_rollout_step(self._h, _lib.ptr(act), _lib.ptr(mi), _lib.ptr(sn),
                                                  _lib.ptr(rs), int(seed), int(offset), _lib.ptr(obs),
-                                                 _lib.ptr(rew), _lib.ptr(done), _lib.stream_ptr()), "step")
+                                                 _lib.ptr(rew), _lib.ptr(done), _lib.stream_ptr(device=self.device)), "step")
         self._keep = self._keep[-8:] + [(act, rs, mi, sn)]
         return obs, rew, done
 
@@ -163,7 +163,7 @@ class EnsembleRollout:
         _lib.check(self._lib.metrpo_rollout_run(
             self._h, T, _lib.ptr(init), _lib.ptr(pool), int(pool.shape[0]), _lib.ptr(ep), _lib.ptr(mi),
             _lib.ptr(sn), int(seed), int(offset), 1 if determ else 0, g("obs"), g("act"), g("mean"),
-            g("rew"), g("done"), _lib.ptr(out["final_states"]), _lib.stream_ptr()), "run")
+            g("rew"), g("done"), _lib.ptr(out["final_states"]), _lib.stream_ptr(device=self.device)), "run")
         self._keep = self._keep[-8:] + [(init, pool, ep, mi, sn)]
         return out
 
@@ -232,13 +232,13 @@ class EnsembleRollout:
         costs = torch.empty(self.K, device=dev)
         _lib.check(self._lib.metrpo_rollout_model_costs(
             self._h, int(n_steps), n, _lib.ptr(init), float(gamma), _lib.ptr(rows), _lib.ptr(costs),
-            _lib.stream_ptr()), "model_costs")
+            _lib.stream_ptr(device=self.device)), "model_costs")
         self._keep = self._keep[-8:] + [(init,)]
         return (costs, rows) if return_rows else costs
 
     def synchronize(self):
         """Wait for the stream and raise if the last kernel aborted on an internal wait timeout."""
-        _lib.check(self._lib.metrpo_rollout_status(self._h, _lib.stream_ptr()), "rollout kernel")
+        _lib.check(self._lib.metrpo_rollout_status(self._h, _lib.stream_ptr(device=self.device)), "rollout kernel")
 
     def last_launches(self):
         return int(self._lib.metrpo_rollout_last_launches(self._h))

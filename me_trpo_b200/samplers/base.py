@@ -17,8 +17,9 @@ def discount_cumsum(x, discount):
 
 
 class BaseSampler:
-    def __init__(self, algo):
+    def __init__(self, algo, dist_ctx=None):
         self.algo = algo
+        self.dist_ctx = dist_ctx          # me_trpo_b200.parallel.DistContext or None (single GPU)
         self._update_kernels = None
 
     def _kernels(self):
@@ -27,6 +28,10 @@ class BaseSampler:
             pol = self.algo.policy
             dims = [pol.obs_dim] + list(pol.hidden_sizes) + [pol.action_dim]
             self._update_kernels = PolicyUpdate(dims, out_tanh=pol.output_tanh, device=pol.device)
+            if self.dist_ctx is not None and self.dist_ctx.distributed:
+                # rows are sharded over ranks: advantage moments and the baseline's normal equations
+                # are summed over the group, so every rank centres / fits on the whole batch
+                self._update_kernels.enable_allreduce(self.dist_ctx.group)
         return self._update_kernels
 
     def process_samples_flat(self, itr, flat):

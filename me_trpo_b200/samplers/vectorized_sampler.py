@@ -9,12 +9,19 @@ import numpy as np
 import torch
 
 from .base import BaseSampler
+from ..parallel import local_reset_pool
 from ..rollout import EnsembleRollout
 
 
 class VectorizedSampler(BaseSampler):
-    def __init__(self, algo, n_envs=None, seed=0, reset_pool_size=None):
-        super().__init__(algo)
+    """`dist_ctx` (parallel.DistContext): with G > 1 ranks the `n_envs` parallel rollouts are
+    block-sharded over the ranks -- rank r owns rows [lo, hi) -- with global-row noise keys and the
+    matching slice of the reset pool, so the union of the ranks' buffers is bit-identical to a
+    single-GPU run; rank 0 draws the global start states from the (real) simulator and broadcasts
+    them, every rank keeps its slice."""
+
+    def __init__(self, algo, n_envs=None, seed=0, reset_pool_size=None, dist_ctx=None):
+        super().__init__(algo, dist_ctx=dist_ctx)
         self.n_envs = n_envs
         self.seed = int(seed)
         self.reset_pool_size = reset_pool_size
@@ -32,14 +39,18 @@ class VectorizedSampler(BaseSampler):
         pol = algo.policy
         if self.rollout is not None:      # the reference rebuilds the vec env every iteration (:23-40)
             self.rollout.close()
-        self.rollout = EnsembleRollout(env.env_name, env.n_models, n_envs, algo.max_path_length,
+        ctx = self.dist_ctx
+        self._lo, self._hi = ctx.shard_rows(n_envs) if ctx is not None else (0, n_envs)
+        if self._hi <= self._lo:
+            raise RuntimeError("more ranks than parallel rollouts (n_envs=%d)" % n_envs)
+        self.rollout = EnsembleRollout(env.env_name, env.n_models, self._hi - self._lo, algo.max_path_length,
                                        hidden=env.hidden, policy_hidden=pol.hidden_sizes,
                                        sam_mode=env.sam_mode, policy_out_tanh=pol.output_tanh,
-                                       device=env.device)
+                                       device=env.device, row_offset=self._lo)
         self.rollout.set_dynamics_ensemble(env.models)
         self.rollout.set_normalization(**env.norm)
         self.env_spec = env.spec
-        self._n_envs = n_envs
+        self._n_envs = n_envs             # GLOBAL number of parallel rollouts
 
     def shutdown_worker(self):
         if self.rollout is not None:
@@ -54,18 +65,34 @@ class VectorizedSampler(BaseSampler):
         rounds = -(-int(algo.batch_size) // per_round)
         return rounds * algo.max_path_length
 
-    def obtain_samples_flat(self, itr, determ=False, n_steps=None, check=True):
-        """Time-major device buffers of one batch.  `check` waits for the kernel and raises if it
-        aborted on an internal wait timeout (the buffers would be partially written); pass False
-        only if the caller checks `self.rollout.synchronize()` itself before consuming them."""
-        algo, env, pol = self.algo, self.algo.env, self.algo.policy
+    def _start_states(self, T):
+        """(init[B_local,S], pool) of this rank: the global draw, sliced to the rank's rows."""
+        algo, env = self.algo, self.algo.env
         B = self._n_envs
-        T = int(n_steps or self._steps_for_batch())
-        self.rollout.set_policy(pol.W, pol.b, pol.log_std)
         n_resets = -(-T // algo.max_path_length)
         R = int(self.reset_pool_size or B * n_resets)
-        init = np.asarray(env.reset_sampler(B), np.float32)          # the initial reset() (:49)
-        pool = np.asarray(env.reset_sampler(R), np.float32)
+        ctx = self.dist_ctx
+        if ctx is None or not ctx.distributed or ctx.rank == 0:      # only rank 0 touches the simulator
+            init = np.asarray(env.reset_sampler(B), np.float32)      # the initial reset() (:49)
+            pool = np.asarray(env.reset_sampler(R), np.float32)
+        else:
+            init = pool = None
+        if ctx is not None and ctx.distributed:
+            init, pool = ctx.broadcast_arrays([init, pool], env.device or "cuda")
+        if self._hi - self._lo != B:
+            pool = local_reset_pool(pool, B, self._lo, self._hi, n_resets)
+            init = init[self._lo:self._hi]
+        return init, pool
+
+    def obtain_samples_flat(self, itr, determ=False, n_steps=None, check=True):
+        """Time-major device buffers of one batch (this rank's rows).  `check` waits for the kernel
+        and raises if it aborted on an internal wait timeout (the buffers would be partially
+        written); pass False only if the caller checks `self.rollout.synchronize()` itself before
+        consuming them."""
+        pol = self.algo.policy
+        T = int(n_steps or self._steps_for_batch())
+        self.rollout.set_policy(pol.W, pol.b, pol.log_std)
+        init, pool = self._start_states(T)
         out = self.rollout.run(T, init, pool, seed=self.seed, offset=self._calls * (1 << 20),
                                determ=determ)
         self._calls += 1
@@ -76,14 +103,10 @@ class VectorizedSampler(BaseSampler):
     def obtain_samples(self, itr, determ=False):
         """The reference's contract (list of completed path dicts on the HOST).  The device->host
         copy of the trajectory is overlapped with the rollout itself (EnsembleRollout.run_to_host)."""
-        algo, env, pol = self.algo, self.algo.env, self.algo.policy
-        B = self._n_envs
+        pol = self.algo.policy
         T = int(self._steps_for_batch())
         self.rollout.set_policy(pol.W, pol.b, pol.log_std)
-        n_resets = -(-T // algo.max_path_length)
-        R = int(self.reset_pool_size or B * n_resets)
-        init = np.asarray(env.reset_sampler(B), np.float32)          # the initial reset() (:49)
-        pool = np.asarray(env.reset_sampler(R), np.float32)
+        init, pool = self._start_states(T)
         host, self._dev_out = self.rollout.run_to_host(T, init, pool, seed=self.seed,
                                                        offset=self._calls * (1 << 20), determ=determ,
                                                        n_chunks=max(1, min(8, T // 32)))

@@ -77,6 +77,10 @@ class PolicyUpdate:
         """obs[T,B,S], rew[T,B], done[T,B] (uint8) device tensors -> dict(adv, ret, valid, stats)."""
         T, B = rew.shape
         dev = self.device
+        if positive_adv and self._cb is not None:
+            # the shift needs the GLOBAL minimum; the accumulator all-reduce is a sum
+            raise NotImplementedError("positive_adv with row-sharded samples (sum all-reduce only); "
+                                      "the reference's TRPO path never sets it (algos/batch_polopt.py:33)")
         assert obs.is_contiguous() and rew.is_contiguous() and done.is_contiguous()
         assert obs.dtype == torch.float32 and rew.dtype == torch.float32 and done.dtype == torch.uint8
         adv = torch.empty(T, B, device=dev)
@@ -87,7 +91,7 @@ class PolicyUpdate:
         _lib.check(self._lib.metrpo_trpo_process(
             self._h, int(T), int(B), _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(done), _lib.ptr(co),
             float(discount), float(gae_lambda), 1 if center_adv else 0, 1 if positive_adv else 0,
-            _lib.ptr(adv), _lib.ptr(ret), _lib.ptr(valid), _lib.ptr(stats), _lib.stream_ptr()), "trpo_process")
+            _lib.ptr(adv), _lib.ptr(ret), _lib.ptr(valid), _lib.ptr(stats), _lib.stream_ptr(device=self.device)), "trpo_process")
         self._keep = self._keep[-4:] + [co]
         return dict(adv=adv, ret=ret, valid=valid, stats=stats)
 
@@ -96,7 +100,7 @@ class PolicyUpdate:
         coeffs = torch.empty(2 * self.S + 4, dtype=torch.float64, device=self.device)
         _lib.check(self._lib.metrpo_trpo_fit_baseline(
             self._h, int(T), int(B), _lib.ptr(obs), _lib.ptr(ret), _lib.ptr(valid), _lib.ptr(done),
-            float(reg_coeff), _lib.ptr(coeffs), _lib.stream_ptr()), "trpo_fit_baseline")
+            float(reg_coeff), _lib.ptr(coeffs), _lib.stream_ptr(device=self.device)), "trpo_fit_baseline")
         return coeffs
 
     # -- R11 ------------------------------------------------------------------------------------
@@ -123,7 +127,7 @@ class PolicyUpdate:
             self._h, int(N), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(adv), _lib.ptr(old_mean),
             _lib.ptr(old_log_std), per_sample, _lib.ptr(valid), _lib.ptr(theta), float(step_size),
             int(cg_iters), float(reg_coeff), float(backtrack_ratio), int(max_backtracks), _lib.ptr(info),
-            _lib.stream_ptr()), "trpo_update")
+            _lib.stream_ptr(device=self.device)), "trpo_update")
         return info
 
     def loss_kl(self, theta, obs, act, adv, old_mean, old_log_std, valid=None):
@@ -131,7 +135,7 @@ class PolicyUpdate:
         out = (ctypes.c_double * 2)()
         _lib.check(self._lib.metrpo_trpo_loss_kl(
             self._h, int(N), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(adv), _lib.ptr(old_mean),
-            _lib.ptr(old_log_std), per_sample, _lib.ptr(valid), _lib.ptr(theta), out, _lib.stream_ptr()),
+            _lib.ptr(old_log_std), per_sample, _lib.ptr(valid), _lib.ptr(theta), out, _lib.stream_ptr(device=self.device)),
             "trpo_loss_kl")
         return float(out[0]), float(out[1])
 
@@ -142,7 +146,7 @@ class PolicyUpdate:
         _lib.check(self._lib.metrpo_trpo_grad(
             self._h, int(N), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(adv), _lib.ptr(old_mean),
             _lib.ptr(old_log_std), per_sample, _lib.ptr(valid), _lib.ptr(theta), _lib.ptr(vec),
-            float(reg_coeff), out.ctypes.data_as(ctypes.c_void_p), _lib.stream_ptr()), "trpo_grad")
+            float(reg_coeff), out.ctypes.data_as(ctypes.c_void_p), _lib.stream_ptr(device=self.device)), "trpo_grad")
         return out
 
     def last_launches(self):

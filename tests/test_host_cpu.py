@@ -170,3 +170,120 @@ def test_sample_trajectories_param_noise_and_scalar_action_noise():
     acts = np.concatenate([np.asarray(a) for a in As])
     assert acts.shape[1] == 2 and np.array_equal(acts[:, 0], acts[:, 1]) and np.abs(acts).max() > 0
     assert info["TimeStepsCollected"] >= 20 and info["avg_weight_change"] == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU host logic of the PRODUCT (me_trpo_b200.parallel.DistContext, the sampler's row
+# sharding, model ownership) over gloo, world size 2
+# ---------------------------------------------------------------------------------------------
+class _FakeRollout:
+    """Stands where EnsembleRollout does: records what the sampler hands to the device."""
+    log = []
+
+    def __init__(self, env, n_models, n_envs, max_path_length, row_offset=0, **kw):
+        self.B, self.row_offset, self.device = n_envs, row_offset, "cpu"
+
+    def set_dynamics_ensemble(self, m): pass
+    def set_normalization(self, **k): pass
+    def set_policy(self, *a): pass
+    def synchronize(self): pass
+    def close(self): pass
+
+    def run(self, T, init, pool, seed=0, offset=0, determ=False):
+        _FakeRollout.log.append(dict(T=T, init=np.array(init), pool=np.array(pool), rows=self.B,
+                                     row_offset=self.row_offset, seed=seed, offset=offset))
+        return {}
+
+
+def _dist_host_worker(rank, world, port, tmp):
+    import types
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from me_trpo_b200.parallel import DistContext, local_reset_pool
+    from me_trpo_b200.policies import GaussianMLPPolicy
+    from me_trpo_b200.samplers import vectorized_sampler as vs
+    ctx = DistContext(rank, world)
+    out = {}
+    # 1. policy broadcast: ranks start from different parameters, end on rank 0's
+    pol = GaussianMLPPolicy(18, 6, (32, 32), device="cpu", seed=100 + rank)
+    ctx.broadcast_policy(pol)
+    out["theta"] = pol.get_param_values()
+    # 2. model ownership + weight exchange: model k is fitted by rank k % G
+    K = 5
+    mine = ctx.my_models(K)
+    local = [dict(W0=torch.full((3, 4), float(k)), b0=torch.full((4,), 10.0 + k)) for k in mine]
+    allm = ctx.gather_models(local, K)
+    out["mine"] = np.asarray(mine)
+    out["gathered"] = np.asarray([[float(m["W0"][0, 0]), float(m["b0"][0])] for m in allm])
+    # 3. rank 0's arrays everywhere
+    arrs = [np.arange(12, dtype=np.float32).reshape(3, 4) + 1, np.asarray([7, 8], np.int64)] if rank == 0 else [None, None]
+    a, b = ctx.broadcast_arrays(arrs, "cpu")
+    out["bc_a"], out["bc_b"] = a, b
+    # 4. the sampler shards rows, keys noise by global row and slices the reset pool; only rank 0
+    #    draws from the simulator
+    draws = []
+    rs = np.random.RandomState(5)
+
+    def reset_sampler(n):
+        draws.append(n)
+        return rs.normal(size=(n, 18)).astype(np.float32)
+    env = types.SimpleNamespace(vectorized=True, env_name="half-cheetah", n_models=K, hidden=256, sam_mode="step_rand",
+                                device="cpu", models=[], norm={}, spec=None, reset_sampler=reset_sampler)
+    algo = types.SimpleNamespace(env=env, policy=types.SimpleNamespace(hidden_sizes=(32, 32), output_tanh=False, W=[], b=[],
+                                                                        log_std=None),
+                                 batch_size=1000, max_path_length=10, discount=1.0, gae_lambda=1.0)
+    vs.EnsembleRollout = _FakeRollout
+    smp = vs.VectorizedSampler(algo, n_envs=37, seed=3, dist_ctx=ctx)
+    smp.start_worker()
+    smp.obtain_samples_flat(0)
+    smp.obtain_samples_flat(1)
+    rec = _FakeRollout.log
+    out["rows"] = np.asarray([r["rows"] for r in rec]); out["row_offset"] = np.asarray([r["row_offset"] for r in rec])
+    out["T"] = np.asarray([r["T"] for r in rec]); out["offsets"] = np.asarray([r["offset"] for r in rec])
+    out["init0"], out["pool0"] = rec[0]["init"], rec[0]["pool"]
+    out["n_draws"] = np.asarray(len(draws))
+    np.savez(os.path.join(tmp, "rank%d.npz" % rank), **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dist_context_and_sharded_sampler_gloo(tmp_path):
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    from me_trpo_b200.parallel import local_reset_pool, shard_rows
+    from me_trpo_b200.policies import GaussianMLPPolicy
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_dist_host_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % i)) for i in range(2)]
+    ref = GaussianMLPPolicy(18, 6, (32, 32), device="cpu", seed=100).get_param_values()
+    np.testing.assert_array_equal(r[0]["theta"], ref)
+    np.testing.assert_array_equal(r[1]["theta"], ref)                 # rank 1 now holds rank 0's policy
+    assert r[0]["mine"].tolist() == [0, 2, 4] and r[1]["mine"].tolist() == [1, 3]
+    want = np.asarray([[k, 10.0 + k] for k in range(5)])
+    np.testing.assert_array_equal(r[0]["gathered"], want)
+    np.testing.assert_array_equal(r[1]["gathered"], want)
+    np.testing.assert_array_equal(r[1]["bc_a"], np.arange(12, dtype=np.float32).reshape(3, 4) + 1)
+    assert r[1]["bc_b"].tolist() == [7, 8]
+    # sampler: 37 rows -> blocks [0,19) and [19,37); T covers batch_size with whole horizons
+    B, T_max = 37, 10
+    T = -(-1000 // (B * T_max)) * T_max
+    for i in range(2):
+        lo, hi = shard_rows(B, i, 2)
+        assert r[i]["rows"].tolist() == [hi - lo] * 2 and r[i]["row_offset"].tolist() == [lo] * 2
+        assert r[i]["T"].tolist() == [T, T] and r[i]["offsets"].tolist() == [0, 1 << 20]
+    assert int(r[0]["n_draws"]) == 4 and int(r[1]["n_draws"]) == 0       # only rank 0 touched the simulator
+    rs = np.random.RandomState(5)
+    n_res = -(-T // T_max)
+    init = rs.normal(size=(B, 18)).astype(np.float32)
+    pool = rs.normal(size=(B * n_res, 18)).astype(np.float32)
+    np.testing.assert_array_equal(np.concatenate([r[0]["init0"], r[1]["init0"]]), init)
+    for i in range(2):
+        lo, hi = shard_rows(B, i, 2)
+        np.testing.assert_array_equal(r[i]["pool0"], local_reset_pool(pool, B, lo, hi, n_res))
+        # the kernel's per-row rule with LOCAL sizes picks the entry the unsharded run would
+        nb = hi - lo
+        for n in range(n_res):
+            for j in (0, nb - 1):
+                np.testing.assert_array_equal(r[i]["pool0"][(n * nb + j) % len(r[i]["pool0"])], pool[(n * B + lo + j) % len(pool)])
