@@ -185,6 +185,10 @@ int metrpo_rollout_get_trace(metrpo_rollout_t* h, unsigned long long* out_host);
 
 /* number of kernels the last run()/step() call launched on the stream (bench gpu_launches) */
 int metrpo_rollout_last_launches(const metrpo_rollout_t* h);
+/* which kernel the last run()/continue() call used: 0 = single-stream rollout_kernel, 1 = two-stream
+ * kernel (rollout_duo.cuh) without column split, 2 = two-stream kernel with the hidden dimension
+ * split over CTA pairs.  Selection is automatic (env METRPO_DUO=0/1/2 overrides, dev switch). */
+int metrpo_rollout_last_kernel(const metrpo_rollout_t* h);
 
 /* Host-only helper (no CUDA call): the gang schedule the library builds for n_tiles row tiles of
  * 128 rows on n_slots gang slots over T steps; out receives n_slots * max_seg quadruples

@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "rollout_kernel.cuh"
+#include "rollout_duo.cuh"
 
 namespace metrpo {
 
@@ -140,7 +141,19 @@ struct metrpo_rollout {
   std::vector<char> dyn_set;
   bool norm_set = false, pol_set = false, state_set = false;
   int last_launches = 0;
+  int last_warps = NUM_THREADS / 32;   // warps per CTA of the last launch (abort diagnostics)
   bool disable_own = false;   // dev / test switch: force the all-candidates exchange
+  // two-stream kernel (rollout_duo.cuh)
+  int duo_mode = -1;          // METRPO_DUO: -1 auto, 0 off, 1 force cs = 1, 2 force cs = 2
+  bool duo_ok = false;        // shapes / TMEM / shared memory allow it
+  int n_pairs = 0;
+  float* duo_pbuf = nullptr; unsigned* duo_pctr = nullptr;
+  float* duo_rbuf = nullptr; unsigned* duo_rctr = nullptr;
+  size_t duo_pbuf_stride = 0, duo_rbuf_stride = 0;
+  uint32_t duo_tm_z = 0;
+  uint32_t d_off_stage, d_off_sw0g, d_off_sw2, d_off_scr[2], d_off_hid[2], d_off_list[2], d_off_sbias,
+      d_off_snorm, d_off_spol, d_off_bars, d_smem_bytes;
+  int last_kernel = 0;        // 0: single-stream, 1: duo cs = 1, 2: duo cs = 2
 };
 
 static uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -150,6 +163,7 @@ static void free_handle(metrpo_rollout* h) {
   cudaFree(h->wstream); cudaFree(h->bias); cudaFree(h->norm); cudaFree(h->pol); cudaFree(h->xbuf);
   cudaFree(h->xctr); cudaFree(h->row_state); cudaFree(h->row_ts); cudaFree(h->row_nreset);
   cudaFree(h->tile_flag); cudaFree(h->dbg); cudaFree(h->trace); cudaFree(h->pm_cost);
+  cudaFree(h->duo_pbuf); cudaFree(h->duo_pctr); cudaFree(h->duo_rbuf); cudaFree(h->duo_rctr);
   for (auto& kv : h->schedules) cudaFree(kv.second);
   delete h;
 }
@@ -314,7 +328,47 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   alloc(reinterpret_cast<void**>(&h->row_nreset), rows_pad * 4);
   alloc(reinterpret_cast<void**>(&h->tile_flag), h->n_tiles * 4);
   alloc(reinterpret_cast<void**>(&h->pm_cost), static_cast<size_t>(c.n_models) * c.n_envs * 4);
-  h->dbg_words = DBG_HEADER + h->max_slots * c.n_models * (NUM_THREADS / 32) * DBG_WORDS_PER_WARP;
+  // ---- two-stream kernel (rollout_duo.cuh): narrow shapes whose second Z operand fits TMEM ----
+  {
+    const char* ev = getenv("METRPO_DUO");
+    h->duo_mode = ev ? atoi(ev) : -1;
+    h->n_pairs = (h->n_tiles + 1) / 2;
+    h->duo_tm_z = h->tm_z;
+    const bool tmem_fits = h->tm_z + 2 * (h->K0 / 2) <= 512;
+    const bool shape_ok = !h->big && c.n_models > 1 && h->n_tiles >= 2 && (h->KC % 2) == 0 &&
+                          2 * c.n_models <= h->num_sms;
+    uint32_t q = 0;
+    h->d_off_stage = q; q += NSTAGE * h->stage_bytes;
+    h->d_off_sw0g = q; q += 2 * h->w0g_bytes;
+    q = align_up(q, 1024); h->d_off_sw2 = q; q += h->w2chunk_bytes;
+    const uint32_t scr_bytes = align_up(std::max(32, c.state_dim + c.action_dim + 1) * TILE_M * 4, 16);
+    for (int g = 0; g < 2; ++g) { h->d_off_scr[g] = q; q += scr_bytes; }
+    for (int g = 0; g < 2; ++g) { h->d_off_hid[g] = q; q += 2 * DUO_POL_ROWS * 33 * 4; }
+    for (int g = 0; g < 2; ++g) { h->d_off_list[g] = q; q += (TILE_M + 4) * 4; }
+    h->d_off_sbias = q; q += (c.hidden + BIAS_PAD) * 4;      // b1 of at most all passes | b2
+    h->d_off_snorm = q; q += align_up((2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4, 16);
+    h->d_off_spol = q; q += align_up(h->pol_floats * 4, 16);
+    h->d_off_bars = q; q += D_NUM_BARS * 8;
+    h->d_smem_bytes = q + 1024;
+    h->duo_ok = shape_ok && tmem_fits && h->d_smem_bytes + 64 <= static_cast<uint32_t>(prop.sharedMemPerBlockOptin) &&
+                h->duo_mode != 0;
+    if (h->duo_ok) {
+      h->duo_pbuf_stride = static_cast<size_t>(c.n_models) * 2 * c.state_dim * TILE_M;
+      h->duo_rbuf_stride = static_cast<size_t>(h->rec_stride) * TILE_M;
+      const size_t streams = static_cast<size_t>(h->n_pairs) * 2;
+      alloc(reinterpret_cast<void**>(&h->duo_pbuf), streams * 2 * h->duo_pbuf_stride * 4);
+      alloc(reinterpret_cast<void**>(&h->duo_pctr), streams * c.n_models * 4);
+      alloc(reinterpret_cast<void**>(&h->duo_rbuf), streams * 2 * h->duo_rbuf_stride * 4);
+      alloc(reinterpret_cast<void**>(&h->duo_rctr), streams * 4);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(rollout_duo_kernel<32, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->d_smem_bytes);
+    }
+  }
+  {
+    const int max_ctas = std::max(h->max_slots * c.n_models, h->num_sms);
+    h->dbg_words = DBG_HEADER + max_ctas * (DUO_THREADS / 32) * DBG_WORDS_PER_WARP;
+  }
   alloc(reinterpret_cast<void**>(&h->dbg), h->dbg_words * 4);
   if (e == cudaSuccess)
     e = h->big ? cudaFuncSetAttribute(rollout_kernel<64, 24, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)
@@ -526,6 +580,66 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
   p.off_stage = h->off_stage; p.off_sw0g = h->off_sw0g; p.off_scr = h->off_scr;
   p.off_sw2 = h->off_sw2; p.off_sbias = h->off_sbias; p.off_snorm = h->off_snorm;
   p.off_spol = h->off_spol; p.off_bars = h->off_bars;
+  // ---- two-stream kernel: pick the column split that keeps the most SMs busy ----
+  if (h->duo_ok && p.own_mode && !p.per_model && p.ext_actions == nullptr) {
+    const int K = c.n_models, NCtot = h->NC;
+    const int old_ctas = std::min(h->n_tiles, h->num_sms / K) * K;
+    int best_cs = 0, best_ctas = 0;
+    for (int cs = 1; cs <= 2; ++cs) {
+      if (NCtot % cs) continue;
+      if (h->duo_mode > 0 && h->duo_mode != cs) continue;
+      const int slots = std::min(h->n_pairs, h->num_sms / (K * cs));
+      if (slots < 1) continue;
+      const int ctas = slots * K * cs;
+      if (ctas > best_ctas) { best_ctas = ctas; best_cs = cs; }
+    }
+    // a duo CTA hides the serial section (~1.2x per SM); below ~0.85 of the single-stream grid it loses
+    if (best_cs && (h->duo_mode > 0 || best_ctas * 20 >= old_ctas * 17)) {
+      DuoParams dpar;
+      std::memset(&dpar, 0, sizeof(dpar));
+      dpar.cs = best_cs; dpar.NCp = NCtot / best_cs; dpar.n_pairs = h->n_pairs;
+      const int slots = best_ctas / (K * best_cs);
+      // schedule over tile PAIRS: key space disjoint from the single-stream schedules
+      const long long key = (static_cast<long long>(0x40000000 | slots) << 32) | static_cast<unsigned>(p.n_steps);
+      const int4* dsegs = nullptr;
+      auto it = h->schedules.find(key);
+      if (it != h->schedules.end()) {
+        dsegs = it->second;
+      } else {
+        std::vector<int4> segs;
+        if (build_schedule_raw(h->n_pairs, slots, p.n_steps, segs) != 0)
+          return set_error(METRPO_ERR_UNSUPPORTED, "run: duo schedule needs more than %d segments per slot", MAX_SEG);
+        int4* d = nullptr;
+        METRPO_CUDA_OK(cudaMalloc(&d, segs.size() * sizeof(int4)));
+        METRPO_CUDA_OK(cudaMemcpy(d, segs.data(), segs.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        h->schedules[key] = d;
+        h->schedule_slots[key] = slots;
+        dsegs = d;
+      }
+      p.segs = dsegs; p.n_slots = slots;
+      p.off_stage = h->d_off_stage; p.off_sw0g = h->d_off_sw0g; p.off_sw2 = h->d_off_sw2;
+      p.off_sbias = h->d_off_sbias; p.off_snorm = h->d_off_snorm; p.off_spol = h->d_off_spol;
+      p.off_bars = h->d_off_bars; p.off_scr = h->d_off_scr[0];
+      dpar.b = p;
+      dpar.pbuf = h->duo_pbuf; dpar.pctr = h->duo_pctr; dpar.pbuf_stride = h->duo_pbuf_stride;
+      dpar.rbuf = h->duo_rbuf; dpar.rctr = h->duo_rctr; dpar.rbuf_stride = h->duo_rbuf_stride;
+      for (int g = 0; g < 2; ++g) {
+        dpar.off_scr[g] = h->d_off_scr[g]; dpar.off_hid[g] = h->d_off_hid[g]; dpar.off_list[g] = h->d_off_list[g];
+      }
+      const size_t streams = static_cast<size_t>(h->n_pairs) * 2;
+      METRPO_CUDA_OK(cudaMemsetAsync(h->duo_pctr, 0, streams * K * 4, st));
+      METRPO_CUDA_OK(cudaMemsetAsync(h->duo_rctr, 0, streams * 4, st));
+      METRPO_CUDA_OK(cudaMemsetAsync(h->tile_flag, 0, h->n_tiles * 4, st));
+      METRPO_CUDA_OK(cudaMemsetAsync(h->dbg, 0, h->dbg_words * 4, st));
+      void* dargs[] = {&dpar};
+      METRPO_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rollout_duo_kernel<32, 8, 256>),
+                                                 dim3(best_ctas), dim3(DUO_THREADS), dargs, h->d_smem_bytes, st));
+      h->last_launches = 1;
+      h->last_warps = DUO_THREADS / 32;
+      h->last_kernel = best_cs;
+      return METRPO_OK;
+    }
+  }
   int n_slots = 0;
   int rc = get_schedule(h, p.n_steps, p.per_model ? p.n_tiles : 0, &p.segs, &n_slots, st);
   if (rc != METRPO_OK) return rc;
@@ -540,6 +654,8 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
                                              dim3(n_slots * c.n_models), dim3(NUM_THREADS), args,
                                              h->smem_bytes, st));
   h->last_launches = 1;
+  h->last_warps = NUM_THREADS / 32;
+  h->last_kernel = 0;
   return METRPO_OK;
 }
 
@@ -628,6 +744,7 @@ extern "C" int metrpo_rollout_step(metrpo_rollout_t* h, const float* actions, co
 }
 
 extern "C" int metrpo_rollout_last_launches(const metrpo_rollout_t* h) { return h ? h->last_launches : 0; }
+extern "C" int metrpo_rollout_last_kernel(const metrpo_rollout_t* h) { return h ? h->last_kernel : 0; }
 
 // Synchronise `stream` and report whether the last launch completed: a kernel whose internal
 // waits timed out sets an abort flag and leaves; the message lists which role of which CTA was
@@ -641,10 +758,11 @@ extern "C" int metrpo_rollout_status(metrpo_rollout_t* h, void* stream_) {
   if (host[0] == 0) return METRPO_OK;
   char msg[480];
   int n = snprintf(msg, sizeof(msg), "rollout kernel aborted (wait timeout):");
-  const int warps = NUM_THREADS / 32;
+  const int warps = h->last_warps;
+  const int n_ctas = (h->dbg_words - DBG_HEADER) / (warps * DBG_WORDS_PER_WARP);
   int shown = 0;
   for (int pass = 1; pass <= 2 && shown < 10; ++pass)   // timed-out waits first, then observers
-    for (int b = 0; b < h->max_slots * h->cfg.n_models && shown < 10; ++b)
+    for (int b = 0; b < n_ctas && shown < 10; ++b)
       for (int w = 0; w < warps && shown < 10; ++w) {
         const unsigned* r = &host[DBG_HEADER + (b * warps + w) * DBG_WORDS_PER_WARP];
         if (r[2] != (unsigned)pass) continue;

@@ -176,7 +176,7 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
 constexpr int DBG_WORDS_PER_WARP = 4;
 constexpr int DBG_HEADER = 16;
 __device__ __forceinline__ void dbg_record(unsigned* dbg, uint32_t tag, uint32_t info, uint32_t why) {
-  const int idx = DBG_HEADER + (blockIdx.x * (NUM_THREADS / 32) + (threadIdx.x >> 5)) * DBG_WORDS_PER_WARP;
+  const int idx = DBG_HEADER + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * DBG_WORDS_PER_WARP;
   dbg[idx + 0] = tag;
   dbg[idx + 1] = info;
   dbg[idx + 2] = why;    // 1 = timed out here, 2 = saw the abort flag here

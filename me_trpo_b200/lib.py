@@ -72,6 +72,7 @@ _PROTOS = {
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "metrpo_rollout_model_costs": (_i, [_vp, _i, _i, _vp, _d, _vp, _vp, _vp]),
     "metrpo_rollout_last_launches": (_i, [_vp]),
+    "metrpo_rollout_last_kernel": (_i, [_vp]),
     "metrpo_rollout_status": (_i, [_vp, _vp]),
     "metrpo_rollout_set_trace": (_i, [_vp, _i, _i, _i]),
     "metrpo_rollout_get_trace": (_i, [_vp, _vp]),

@@ -242,3 +242,7 @@ class EnsembleRollout:
 
     def last_launches(self):
         return int(self._lib.metrpo_rollout_last_launches(self._h))
+
+    def last_kernel(self):
+        """0: single-stream kernel, 1 / 2: two-stream kernel without / with column split."""
+        return int(self._lib.metrpo_rollout_last_kernel(self._h))

@@ -239,3 +239,98 @@ def test_run_to_host_chunked_equals_single_launch(n_chunks):
         np.testing.assert_array_equal(host[k].numpy(), ref[k], err_msg=k)
     assert ref["done"].sum() == B * (T // T_max)
     ro.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# two-stream kernel (csrc/rollout_duo.cuh): forced through the METRPO_DUO dev switch, which the
+# library reads when a handle is created
+# ---------------------------------------------------------------------------------------------
+DUO = [
+    # ragged: 5 tiles -> 3 tile pairs (the last pair has one dummy tile), resets inside the horizon
+    ("duo_hc_philox", "half-cheetah", 5, 600, 7, 4, 512, "step_rand", "philox"),
+    ("duo_hc_explicit", "half-cheetah", 3, 256, 5, 100, 512, "step_rand", "explicit"),
+    ("duo_hc_eps_rand", "half-cheetah", 4, 384, 6, 3, 1024, "eps_rand", "philox"),
+    ("duo_hopper", "hopper", 3, 300, 5, 3, 512, "step_rand", "explicit"),
+    ("duo_swimmer", "swimmer", 5, 700, 6, 5, 512, "step_rand", "philox"),
+    # more pairs than gang slots: chains cut across slots, tile state handed over through row_state
+    ("duo_hc_many_tiles", "half-cheetah", 5, 4096, 9, 100, 512, "step_rand", "philox"),
+]
+
+
+def _with_duo(mode, fn):
+    old = os.environ.get("METRPO_DUO")
+    os.environ["METRPO_DUO"] = str(mode)
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("METRPO_DUO", None)
+        else:
+            os.environ["METRPO_DUO"] = old
+
+
+def _device_run_kernel(case, inp=None, **kw):
+    """(results, inputs, kernel id) of one fused launch."""
+    from me_trpo_b200.rollout import EnsembleRollout
+    name, env, K, B, T, T_max, hidden, sam_mode, noise_kind = case
+    inp = inp or mg.make_inputs(env, K, B, T, hidden)
+    ro = EnsembleRollout(env, K, B, T_max, hidden=hidden, sam_mode=sam_mode)
+    ro.set_dynamics_ensemble(inp["models"]); ro.set_normalization(**inp["norm"])
+    ro.set_policy(inp["pol"]["W"], inp["pol"]["b"], inp["pol"]["log_std"])
+    rk = dict(seed=1234, offset=7)
+    if noise_kind == "explicit":
+        rk.update(eps=inp["eps"], model_idx=inp["mi"])
+    rk.update(kw)
+    out = ro.run(T, inp["init"], inp["pool"], **rk)
+    ro.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    kern = ro.last_kernel()
+    ro.close()
+    return res, inp, kern
+
+
+@pytest.mark.parametrize("cs", [1, 2])
+@pytest.mark.parametrize("case", DUO, ids=[c[0] for c in DUO])
+def test_duo_kernel_matches_oracle_and_single_stream(case, cs):
+    name, env, K, B, T, T_max, hidden, sam_mode, noise_kind = case
+    if cs == 2 and (hidden // 256) % 2:
+        pytest.skip("column split needs an even number of layer-1 passes")
+    duo, inp, kern = _with_duo(cs, lambda: _device_run_kernel(case))
+    assert kern == cs, "the two-stream kernel was not selected"
+    single, _, kern0 = _with_duo(0, lambda: _device_run_kernel(case, inp=inp))
+    assert kern0 == 0
+    noise = (orl.PhiloxNoise(1234, 7, 0, sam_mode) if noise_kind == "philox"
+             else orl.ExplicitNoise(inp["eps"], inp["mi"], inp["sn"]))
+    ref = orl.rollout_flat(env, inp["pol"], inp["models"], inp["norm"], inp["init"], inp["pool"], noise, T,
+                           T_max, sam_mode, mma="bf16")
+    for k in ("obs", "act", "mean", "rew", "final_states"):
+        assert np.max(np.abs(duo[k] - ref[k])) <= TOL_BF16, (name, cs, k)
+        if cs == 1:     # same arithmetic in the same order: bit-identical to the single-stream kernel
+            np.testing.assert_array_equal(duo[k], single[k])
+        else:           # layer-2 partial sums of the two column halves are added in a different order
+            assert np.max(np.abs(duo[k] - single[k])) <= 2e-5, (name, k)
+    assert np.array_equal(duo["done"], ref["done"]) and np.array_equal(duo["done"], single["done"])
+
+
+@pytest.mark.parametrize("cs", [1, 2])
+def test_duo_kernel_chained_launches_equal_single_launch(cs):
+    """metrpo_rollout_continue through the two-stream kernel: the state handed over in row_state
+    makes an 3-chunk run bit-identical to one launch."""
+    from me_trpo_b200.rollout import EnsembleRollout
+    case = DUO[0]
+    name, env, K, B, T, T_max, hidden, sam_mode, _ = case
+
+    def go():
+        inp = mg.make_inputs(env, K, B, T, hidden)
+        ro = EnsembleRollout(env, K, B, T_max, hidden=hidden, sam_mode=sam_mode)
+        ro.set_dynamics_ensemble(inp["models"]); ro.set_normalization(**inp["norm"])
+        ro.set_policy(inp["pol"]["W"], inp["pol"]["b"], inp["pol"]["log_std"])
+        one = ro.run(T, inp["init"], inp["pool"], seed=9, offset=3); ro.synchronize()
+        one = {k: v.cpu().numpy() for k, v in one.items()}
+        host, _ = ro.run_to_host(T, inp["init"], inp["pool"], seed=9, offset=3, n_chunks=3); ro.synchronize()
+        assert ro.last_kernel() == cs
+        ro.close()
+        return one, {k: v.numpy() for k, v in host.items()}
+    one, chunked = _with_duo(cs, go)
+    for k in ("obs", "act", "mean", "rew", "done", "final_states"):
+        np.testing.assert_array_equal(one[k], chunked[k])
