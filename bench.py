@@ -271,6 +271,7 @@ def run_cuda(args, rank, local_rank, world):
         return float(tot.item()), ms, sampler.summary()
 
     total_ms, per_step, clocks = timed(False)
+    kernel_variant = ro.last_kernel()
     total_ms_e2e, _, _ = timed(True)
     finite = bool(torch.isfinite(out["obs"]).all().item()) and bool(torch.isfinite(host_out["obs"]).all().item())
 
@@ -361,6 +362,7 @@ def run_cuda(args, rank, local_rank, world):
                             "trajectory (obs, act, mean, rew, done) -> pinned host, copy of finished steps "
                             "overlapped with the remaining horizon (EnsembleRollout.run_to_host)" % E2E_CHUNKS},
             "gpu_launches": args.steps * ro.last_launches(),
+            "rollout_kernel_variant": {0: "single-stream", 1: "two-stream", 2: "two-stream, column split"}[kernel_variant],
             "clocks": clocks, "finite": finite, "trpo_half_of_iteration": trpo_info,
         }
         print(json.dumps(line), flush=True)

@@ -334,7 +334,7 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     h->duo_mode = ev ? atoi(ev) : -1;
     h->n_pairs = (h->n_tiles + 1) / 2;
     h->duo_tm_z = h->tm_z;
-    const bool tmem_fits = h->tm_z + 2 * (h->K0 / 2) <= 512;
+    const bool tmem_fits = h->tm_z + (h->K0 / 2) <= 512;          // one Z slot always; two when they fit
     const bool shape_ok = !h->big && c.n_models > 1 && h->n_tiles >= 2 && (h->KC % 2) == 0 &&
                           2 * c.n_models <= h->num_sms;
     uint32_t q = 0;
@@ -593,11 +593,16 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
       const int ctas = slots * K * cs;
       if (ctas > best_ctas) { best_ctas = ctas; best_cs = cs; }
     }
-    // a duo CTA hides the serial section (~1.2x per SM); below ~0.85 of the single-stream grid it loses
-    if (best_cs && (h->duo_mode > 0 || best_ctas * 20 >= old_ctas * 17)) {
+    // Measured on B200 (tools/duo_probe.py, profiles/r2_duo_probe.json): without column split a
+    // two-stream CTA needs ~12 % fewer cycles per tile-step than a single-stream one; with the
+    // column split the extra stream switches eat the gain (half-cheetah K = 5, B = 4096: 80.8 k vs
+    // 84 k cycles per tile-step on 140 instead of 145 SMs = a tie).  Automatic selection therefore
+    // takes the two-stream kernel only unsplit and only when it keeps as many SMs busy.
+    if (best_cs && (h->duo_mode > 0 || (best_cs == 1 && best_ctas >= old_ctas))) {
       DuoParams dpar;
       std::memset(&dpar, 0, sizeof(dpar));
       dpar.cs = best_cs; dpar.NCp = NCtot / best_cs; dpar.n_pairs = h->n_pairs;
+      dpar.z_shared = (h->tm_z + 2 * (h->K0 / 2) > 512) ? 1 : 0;
       const int slots = best_ctas / (K * best_cs);
       // schedule over tile PAIRS: key space disjoint from the single-stream schedules
       const long long key = (static_cast<long long>(0x40000000 | slots) << 32) | static_cast<unsigned>(p.n_steps);

@@ -64,7 +64,8 @@ enum {
   D_ACC2FREE = 23,   // acc2 loaded to registers (128 arrivals): the other stream's L2 may overwrite it
   D_ZREADY = 24,     // [2 streams] Z operand written (128 arrivals)
   D_START = 26,      // [2 streams] first L0 group of the stream-step retired (commit)
-  D_NUM_BARS = 28
+  D_ZFREE = 28,      // z_shared: every L0 of a stream-step retired (commit): the single Z slot may be rewritten
+  D_NUM_BARS = 29
 };
 
 struct DuoParams {
@@ -79,6 +80,8 @@ struct DuoParams {
   unsigned* rctr;               // [slot*2 + stream]
   unsigned long long rbuf_stride;
   uint32_t off_scr[2], off_hid[2], off_list[2];   // per-stream shared memory areas
+  int z_shared;                 // 1: TMEM has room for ONE Z operand only (K0 = 48, ant): the streams take
+                                //    turns, a group writes its Z after the other stream's last L0 retired
 };
 
 // Fully inlined bounded waits: a register-re-partitioned region (setmaxnreg) must not contain ABI
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
     for (int i = 0; i < 4; ++i) mbar_init(&bars[D_H1FULL + i], EPI_THREADS);
     mbar_init(&bars[D_ACC1FULL], 1);
     mbar_init(&bars[D_ACC2FULL], 1);
+    mbar_init(&bars[D_ZFREE], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
@@ -193,7 +197,8 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t zcols = static_cast<uint32_t>(p.K0 / 2);   // TMEM columns of one stream's Z operand
+  // TMEM columns between the two streams' Z operands (0: one shared slot)
+  const uint32_t zcols = dp.z_shared ? 0u : static_cast<uint32_t>(p.K0 / 2);
 
   if (warp < 4) {
     setmaxnreg_dec_lo();
@@ -319,6 +324,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
               for (int j = 0; j < k0steps; ++j)
                 umma_ts(acc0, ztm + j * 8, w0desc0 + (gg & 1) * w0slot + j * w0_kstep, idesc0, j > 0);
               umma_commit(&bars[D_ACC0FULL + (gg & 1)]);
+              if (G + 2 == NGSp) umma_commit(&bars[D_ZFREE]);   // that was the stream-step's last L0
             }
             const uint32_t at = tmem + p.tm_h0;
             const uint64_t bd = stdesc0 + s * ststride;
@@ -526,6 +532,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
               const float uu = fminf(fmaxf(a_raw[i], -1.f), 1.f);   // env_helpers.py:599
               scrA[(S + i) * TILE_M + r] = __fmul_rn(__fsub_rn(uu, inMean[S + i]), inRstd[S + i]);
             }
+          if (dp.z_shared && u > 0) DWAITB(D_ZFREE, (u - 1) & 1);   // the other stream's L0s are done with the slot
           for (int cc = 0; cc < p.K0 / 16; ++cc) {
             uint32_t pk[8];
 #pragma unroll
