@@ -57,7 +57,13 @@ enum {
   METRPO_SAM_ONE_MODEL = 5
 };
 
-enum { METRPO_PREC_BF16 = 0 }; /* tensor-core input type; accumulation and epilogues are fp32 */
+/* arithmetic of the dynamics MLP:
+ *   METRPO_PREC_BF16  tcgen05 tensor cores, bf16 operands, fp32 accumulation and epilogues (fast path)
+ *   METRPO_PREC_FP32  fp32 FMA on CUDA cores with the reference's operation order (true division by
+ *                     in_std, tanhf): the reference's tf.matmul arithmetic (training.py:207-208), ~50x
+ *                     slower; a fidelity mode to measure what the bf16 operands cost (all sam_modes,
+ *                     run / continue / step / model_costs). */
+enum { METRPO_PREC_BF16 = 0, METRPO_PREC_FP32 = 1 };
 
 #define METRPO_MAX_POLICY_LAYERS 4
 

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "rollout_kernel.cuh"
 #include "rollout_duo.cuh"
+#include "rollout_fp32.cuh"
 
 namespace metrpo {
 
@@ -153,7 +154,12 @@ struct metrpo_rollout {
   uint32_t duo_tm_z = 0;
   uint32_t d_off_stage, d_off_sw0g, d_off_sw2, d_off_scr[2], d_off_hid[2], d_off_list[2], d_off_sbias,
       d_off_snorm, d_off_spol, d_off_bars, d_smem_bytes;
-  int last_kernel = 0;        // 0: single-stream, 1: duo cs = 1, 2: duo cs = 2
+  int last_kernel = 0;        // 0: single-stream, 1: duo cs = 1, 2: duo cs = 2, 3: fp32 fidelity path
+  // fp32 fidelity mode (rollout_fp32.cuh): raw weights + per-step activations
+  bool fp32 = false;
+  float *f_W0 = nullptr, *f_b0 = nullptr, *f_W1 = nullptr, *f_b1 = nullptr, *f_W2 = nullptr, *f_b2 = nullptr;
+  float *f_x = nullptr, *f_aclip = nullptr, *f_araw = nullptr, *f_z = nullptr, *f_h0 = nullptr, *f_h1 = nullptr,
+        *f_o = nullptr, *f_pm = nullptr;
 };
 
 static uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -164,6 +170,9 @@ static void free_handle(metrpo_rollout* h) {
   cudaFree(h->xctr); cudaFree(h->row_state); cudaFree(h->row_ts); cudaFree(h->row_nreset);
   cudaFree(h->tile_flag); cudaFree(h->dbg); cudaFree(h->trace); cudaFree(h->pm_cost);
   cudaFree(h->duo_pbuf); cudaFree(h->duo_pctr); cudaFree(h->duo_rbuf); cudaFree(h->duo_rctr);
+  cudaFree(h->f_W0); cudaFree(h->f_b0); cudaFree(h->f_W1); cudaFree(h->f_b1); cudaFree(h->f_W2); cudaFree(h->f_b2);
+  cudaFree(h->f_x); cudaFree(h->f_aclip); cudaFree(h->f_araw); cudaFree(h->f_z); cudaFree(h->f_h0); cudaFree(h->f_h1);
+  cudaFree(h->f_o); cudaFree(h->f_pm);
   for (auto& kv : h->schedules) cudaFree(kv.second);
   delete h;
 }
@@ -180,9 +189,11 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     return set_error(METRPO_ERR_INVALID, "create: unknown env_id %d", c.env_id);
   if (c.sam_mode < METRPO_SAM_STEP_RAND || c.sam_mode > METRPO_SAM_ONE_MODEL)
     return set_error(METRPO_ERR_INVALID, "create: unknown sam_mode %d", c.sam_mode);
-  if (c.precision != METRPO_PREC_BF16)
-    return set_error(METRPO_ERR_UNSUPPORTED, "create: only METRPO_PREC_BF16 is implemented");
-  {
+  if (c.precision != METRPO_PREC_BF16 && c.precision != METRPO_PREC_FP32)
+    return set_error(METRPO_ERR_UNSUPPORTED, "create: precision must be METRPO_PREC_BF16 or METRPO_PREC_FP32");
+  const bool fp32 = (c.precision == METRPO_PREC_FP32);
+  if (fp32 && c.hidden < 1) return set_error(METRPO_ERR_INVALID, "create: hidden >= 1 required");
+  if (!fp32) {
     bool big = c.state_dim > 32 || c.action_dim > 8;
     for (int l = 1; l < c.n_policy_layers && l < METRPO_MAX_POLICY_LAYERS; ++l) big = big || c.policy_dims[l] > HPB;
     const int mult = big ? 128 : 256;
@@ -213,6 +224,7 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
 
   metrpo_rollout* h = new metrpo_rollout();
   h->cfg = c;
+  h->fp32 = fp32;
   h->num_sms = prop.multiProcessorCount;
   h->Din = c.state_dim + c.action_dim - c.drop_cols;
   h->K0 = static_cast<int>(align_up(h->Din + 2, 16));   // +2: ones columns carrying b0 (hi, lo)
@@ -228,8 +240,8 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   h->tm_acc2 = h->tm_acc0 + 128;
   h->tm_h0 = h->tm_acc2 + std::max(h->S_pad, 32);
   h->tm_z = h->tm_h0 + 64;
-  h->NC = c.hidden / h->N1;
-  h->KC = c.hidden / 64;
+  h->NC = std::max(1, c.hidden / h->N1);
+  h->KC = std::max(2, c.hidden / 64);
   h->n_tiles = (c.n_envs + TILE_M - 1) / TILE_M;
   h->max_slots = std::min(h->n_tiles, h->num_sms / c.n_models);
   h->w0g_bytes = 128 * h->K0 * 2;
@@ -299,12 +311,12 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
   h->off_spol = o; o += h->pol_in_smem ? align_up(h->pol_floats * 4, 16) : 0;
   h->off_bars = o; o += NUM_BARS * 8;
   h->smem_bytes = o + 1024;
-  if (h->smem_bytes > static_cast<uint32_t>(prop.sharedMemPerBlockOptin)) {
+  if (!fp32 && h->smem_bytes > static_cast<uint32_t>(prop.sharedMemPerBlockOptin)) {
     int need = h->smem_bytes;
     delete h;
     return set_error(METRPO_ERR_UNSUPPORTED, "create: config needs %d B of shared memory per CTA (limit %d)", need, (int)prop.sharedMemPerBlockOptin);
   }
-  if (h->tm_z + h->K0 / 2 > 512) {
+  if (!fp32 && h->tm_z + h->K0 / 2 > 512) {
     delete h;
     return set_error(METRPO_ERR_UNSUPPORTED, "create: TMEM budget exceeded (S_pad %d, padded dynamics input %d)", h->S_pad, h->K0);
   }
@@ -315,7 +327,18 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
     if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
   };
-  alloc(reinterpret_cast<void**>(&h->wstream), h->model_stride * c.n_models);
+  if (fp32) {   // raw weights and per-step activations of the fidelity path
+    const size_t K = c.n_models, H = c.hidden, B = c.n_envs, S = c.state_dim, A = c.action_dim, Din = h->Din;
+    alloc(reinterpret_cast<void**>(&h->f_W0), K * Din * H * 4); alloc(reinterpret_cast<void**>(&h->f_b0), K * H * 4);
+    alloc(reinterpret_cast<void**>(&h->f_W1), K * H * H * 4); alloc(reinterpret_cast<void**>(&h->f_b1), K * H * 4);
+    alloc(reinterpret_cast<void**>(&h->f_W2), K * H * S * 4); alloc(reinterpret_cast<void**>(&h->f_b2), K * S * 4);
+    alloc(reinterpret_cast<void**>(&h->f_x), K * B * S * 4); alloc(reinterpret_cast<void**>(&h->f_aclip), K * B * A * 4);
+    alloc(reinterpret_cast<void**>(&h->f_araw), K * B * A * 4);
+    alloc(reinterpret_cast<void**>(&h->f_z), K * B * Din * 4);
+    alloc(reinterpret_cast<void**>(&h->f_h0), K * B * H * 4); alloc(reinterpret_cast<void**>(&h->f_h1), K * B * H * 4);
+    alloc(reinterpret_cast<void**>(&h->f_o), K * B * S * 4); alloc(reinterpret_cast<void**>(&h->f_pm), 3 * K * B * 4);
+  }
+  alloc(reinterpret_cast<void**>(&h->wstream), fp32 ? 1024 : h->model_stride * c.n_models);
   alloc(reinterpret_cast<void**>(&h->bias), static_cast<size_t>(c.n_models) * (2 * c.hidden + BIAS_PAD) * 4);
   alloc(reinterpret_cast<void**>(&h->norm), (2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4);
   alloc(reinterpret_cast<void**>(&h->pol), h->pol_floats * 4);
@@ -335,7 +358,7 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     h->n_pairs = (h->n_tiles + 1) / 2;
     h->duo_tm_z = h->tm_z;
     const bool tmem_fits = h->tm_z + (h->K0 / 2) <= 512;          // one Z slot always; two when they fit
-    const bool shape_ok = !h->big && c.n_models > 1 && h->n_tiles >= 2 && (h->KC % 2) == 0 &&
+    const bool shape_ok = !fp32 && !h->big && c.n_models > 1 && h->n_tiles >= 2 && (h->KC % 2) == 0 &&
                           2 * c.n_models <= h->num_sms;
     uint32_t q = 0;
     h->d_off_stage = q; q += NSTAGE * h->stage_bytes;
@@ -370,7 +393,7 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     h->dbg_words = DBG_HEADER + max_ctas * (DUO_THREADS / 32) * DBG_WORDS_PER_WARP;
   }
   alloc(reinterpret_cast<void**>(&h->dbg), h->dbg_words * 4);
-  if (e == cudaSuccess)
+  if (e == cudaSuccess && !fp32)
     e = h->big ? cudaFuncSetAttribute(rollout_kernel<64, 24, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)
                : cudaFuncSetAttribute(rollout_kernel<32, 8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
   if (e != cudaSuccess) {
@@ -397,6 +420,17 @@ extern "C" int metrpo_rollout_set_dynamics(metrpo_rollout_t* h, int k, const flo
   if (!W0 || !b0 || !W1 || !b1 || !W2 || !b2) return set_error(METRPO_ERR_INVALID, "set_dynamics: null weight pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   const int H = h->cfg.hidden, S = h->cfg.state_dim;
+  if (h->fp32) {
+    const size_t Din = h->Din;
+    auto cp = [&](float* dst, const float* src, size_t n) {
+      return cudaMemcpyAsync(dst + static_cast<size_t>(k) * n, src, n * 4, cudaMemcpyDeviceToDevice, st);
+    };
+    METRPO_CUDA_OK(cp(h->f_W0, W0, Din * H)); METRPO_CUDA_OK(cp(h->f_b0, b0, H));
+    METRPO_CUDA_OK(cp(h->f_W1, W1, static_cast<size_t>(H) * H)); METRPO_CUDA_OK(cp(h->f_b1, b1, H));
+    METRPO_CUDA_OK(cp(h->f_W2, W2, static_cast<size_t>(H) * S)); METRPO_CUDA_OK(cp(h->f_b2, b2, S));
+    h->dyn_set[k] = 1;
+    return METRPO_OK;
+  }
   uint8_t* dst = h->wstream + static_cast<size_t>(k) * h->model_stride;
   const int T = 256;
   pack_w1_kernel<<<(static_cast<size_t>(H) * H + T - 1) / T, T, 0, st>>>(W1, dst, H, h->KC, h->N1, h->stage_bytes);
@@ -549,11 +583,79 @@ static int get_schedule(metrpo_rollout* h, int T, int whole_tiles, const int4** 
   return METRPO_OK;
 }
 
+// fp32 fidelity path (rollout_fp32.cuh): the same step semantics, one launch per layer and step
+static int launch_fp32(metrpo_rollout* h, const KParams& kp, cudaStream_t st) {
+  const metrpo_rollout_cfg& c = h->cfg;
+  const int K = c.n_models, S = c.state_dim, A = c.action_dim, H = c.hidden, Din = h->Din;
+  const int B = kp.per_model ? kp.B : c.n_envs;
+  const int sets = kp.per_model ? K : 1;
+  Fp32Params p;
+  std::memset(&p, 0, sizeof(p));
+  p.S = S; p.A = A; p.SA = S + A; p.drop = c.drop_cols; p.Din = Din; p.H = H; p.K = K; p.B = B;
+  p.T_max = c.max_path_length; p.env_id = c.env_id; p.sam_mode = c.sam_mode; p.determ = kp.determ;
+  p.per_model = kp.per_model; p.n_pol_layers = c.n_policy_layers; p.pol_out_tanh = c.policy_out_tanh;
+  p.pol_logstd_off = h->pol_logstd_off; p.row_offset = c.row_offset;
+  for (int l = 0; l < 4; ++l) p.pl[l] = h->pl[l];
+  p.pol = h->pol; p.norm = h->norm; p.gamma = kp.gamma;
+  p.eps = kp.eps; p.model_idx = kp.model_idx; p.std_noise = kp.std_noise;
+  p.ext_actions = kp.ext_actions; p.ext_reset_states = kp.ext_reset_states;
+  p.reset_pool = kp.reset_pool; p.R = kp.R > 0 ? kp.R : 1; p.seed = kp.seed; p.offset = kp.offset;
+  p.ts = h->row_ts; p.nreset = h->row_nreset;
+  p.a_clip = h->f_aclip; p.a_raw = h->f_araw; p.z = h->f_z; p.o = h->f_o;
+  p.pm_acc = h->f_pm; p.pm_gpow = h->f_pm + static_cast<size_t>(K) * c.n_envs; p.pm_dmask = h->f_pm + 2 * static_cast<size_t>(K) * c.n_envs;
+  p.obs = kp.obs; p.act = kp.act; p.mean = kp.mean; p.rew = kp.rew; p.done = kp.done;
+  const int TPB = 128;
+  const size_t nstate = static_cast<size_t>(B) * S;
+  if (kp.per_model) {   // every model rolls its own copy of the start states
+    p.x = h->f_x;
+    fp32_tile_states<<<(nstate * K + 255) / 256, 256, 0, st>>>(kp.init_states, h->f_x, K, nstate);
+    const size_t n = static_cast<size_t>(K) * B;
+    fp32_fill<<<(n + 255) / 256, 256, 0, st>>>(p.pm_acc, 0.f, n);
+    fp32_fill<<<(n + 255) / 256, 256, 0, st>>>(p.pm_gpow, 1.f, n);
+    fp32_fill<<<(n + 255) / 256, 256, 0, st>>>(p.pm_dmask, 0.f, n);
+  } else {
+    p.x = h->row_state;
+    if (!kp.resume) {
+      const int rows_pad = h->n_tiles * TILE_M;
+      const int n = std::max(B * S, rows_pad);
+      reset_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(kp.init_states, h->row_state, h->row_ts, h->row_nreset, B, S, rows_pad);
+    }
+  }
+  const int rows = sets * B;
+  const dim3 g0((H + 63) / 64, (B + 63) / 64, K), g2((S + 63) / 64, (B + 63) / 64, K);
+  int launches = 0;
+  for (int t = 0; t < kp.n_steps; ++t) {
+    p.t = t;
+    fp32_begin_step<<<(rows + TPB - 1) / TPB, TPB, 0, st>>>(p);
+    fp32_gemm_bias_act<<<g0, 256, 0, st>>>(h->f_z, kp.per_model ? static_cast<long long>(B) * Din : 0LL, h->f_W0,
+                                           static_cast<long long>(Din) * H, h->f_b0, H, h->f_h0,
+                                           static_cast<long long>(B) * H, B, H, Din, 1);
+    fp32_gemm_bias_act<<<g0, 256, 0, st>>>(h->f_h0, static_cast<long long>(B) * H, h->f_W1, static_cast<long long>(H) * H,
+                                           h->f_b1, H, h->f_h1, static_cast<long long>(B) * H, B, H, H, 1);
+    fp32_gemm_bias_act<<<g2, 256, 0, st>>>(h->f_h1, static_cast<long long>(B) * H, h->f_W2, static_cast<long long>(H) * S,
+                                           h->f_b2, S, h->f_o, static_cast<long long>(B) * S, B, S, H, 0);
+    if (h->big) fp32_finish_step<64, 24><<<(rows + TPB - 1) / TPB, TPB, 0, st>>>(p);
+    else fp32_finish_step<32, 8><<<(rows + TPB - 1) / TPB, TPB, 0, st>>>(p);
+    launches += 5;
+  }
+  METRPO_CUDA_OK(cudaGetLastError());
+  if (kp.per_model) {
+    METRPO_CUDA_OK(cudaMemcpyAsync(kp.pm_cost, p.pm_acc, static_cast<size_t>(K) * B * 4, cudaMemcpyDeviceToDevice, st));
+  } else if (kp.final_states) {
+    METRPO_CUDA_OK(cudaMemcpyAsync(kp.final_states, h->row_state, nstate * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  METRPO_CUDA_OK(cudaMemsetAsync(h->dbg, 0, 4, st));
+  h->last_launches = launches;
+  h->last_kernel = 3;
+  return METRPO_OK;
+}
+
 static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
   for (int k = 0; k < h->cfg.n_models; ++k)
     if (!h->dyn_set[k]) return set_error(METRPO_ERR_STATE, "run: dynamics model %d was never set", k);
   if (!h->norm_set) return set_error(METRPO_ERR_STATE, "run: normalization constants were never set");
   const metrpo_rollout_cfg& c = h->cfg;
+  if (h->fp32) return launch_fp32(h, p, st);
   p.S = c.state_dim; p.A = c.action_dim; p.SA = p.S + p.A; p.drop = c.drop_cols; p.Din = h->Din;
   p.K0 = h->K0; p.H = c.hidden; p.S_pad = h->S_pad; p.K = c.n_models;
   if (!p.per_model) p.B = c.n_envs;

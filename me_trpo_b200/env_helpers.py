@@ -21,7 +21,7 @@ class NeuralNetEnv:
     vec_env_executor (samplers/vectorized_sampler.py:29-33)."""
 
     def __init__(self, env, models, norm, sam_mode="step_rand", reset_sampler=None, hidden=None,
-                 device=None, policy_hidden=None):
+                 device=None, policy_hidden=None, precision="bf16"):
         self.vectorized = True
         self.env_name = canonical_env_name(env)
         spec = ENV_SPECS[self.env_name]
@@ -32,6 +32,7 @@ class NeuralNetEnv:
         self.hidden = int(hidden or self.models[0]["W1"].shape[0])
         self.policy_hidden = policy_hidden
         self.device = device
+        self.precision = precision     # "bf16" (tensor cores) | "fp32" (reference arithmetic, slow)
         self.reset_sampler = reset_sampler or (
             lambda n: np.random.normal(0.0, 0.1, size=(n, self.S)).astype(np.float32))
         self._single = None
@@ -78,7 +79,8 @@ class VecSimpleEnv:
         self.rng = np.random if rng is None else rng
         self.rollout = EnsembleRollout(env.env_name, env.n_models, self.n_envs, self.max_path_length,
                                        hidden=env.hidden, sam_mode=env.sam_mode, device=env.device,
-                                       policy_hidden=env.policy_hidden)
+                                       policy_hidden=env.policy_hidden,
+                                       precision=getattr(env, "precision", "bf16"))
         self.rollout.set_dynamics_ensemble(env.models)
         self.rollout.set_normalization(**env.norm)
         self.device = self.rollout.device

@@ -84,7 +84,7 @@ class PolicyCostEvaluator:
         self.rollout = EnsembleRollout(env.env_name, env.n_models, int(n_rows), self.T,
                                        hidden=env.hidden, policy_hidden=policy.hidden_sizes,
                                        sam_mode=env.sam_mode, policy_out_tanh=policy.output_tanh,
-                                       device=env.device)
+                                       device=env.device, precision=getattr(env, "precision", "bf16"))
         self.refresh_models()
 
     def refresh_models(self):

@@ -22,7 +22,7 @@ class EnsembleRollout:
 
     def __init__(self, env, n_models, n_envs, max_path_length, hidden=None, policy_hidden=None,
                  sam_mode="step_rand", drop_cols=None, policy_out_tanh=False, device=None,
-                 state_dim=None, action_dim=None, row_offset=0):
+                 state_dim=None, action_dim=None, row_offset=0, precision="bf16"):
         name = canonical_env_name(env)
         spec = ENV_SPECS[name]
         self.env_name = name
@@ -52,7 +52,10 @@ class EnsembleRollout:
         for i, d in enumerate(dims):
             cfg.policy_dims[i] = d
         cfg.policy_out_tanh = 1 if policy_out_tanh else 0
-        cfg.precision = 0
+        # "bf16": tcgen05 tensor cores (bf16 operands, fp32 accumulate); "fp32": the reference's fp32
+        # arithmetic on CUDA cores, ~50x slower (fidelity mode, include/metrpo.h METRPO_PREC_FP32)
+        self.precision = precision
+        cfg.precision = {"bf16": 0, "fp32": 1}[precision]
         cfg.row_offset = int(row_offset)
         cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._h = ctypes.c_void_p()

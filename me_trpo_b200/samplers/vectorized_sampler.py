@@ -46,7 +46,8 @@ class VectorizedSampler(BaseSampler):
         self.rollout = EnsembleRollout(env.env_name, env.n_models, self._hi - self._lo, algo.max_path_length,
                                        hidden=env.hidden, policy_hidden=pol.hidden_sizes,
                                        sam_mode=env.sam_mode, policy_out_tanh=pol.output_tanh,
-                                       device=env.device, row_offset=self._lo)
+                                       device=env.device, row_offset=self._lo,
+                                       precision=getattr(env, "precision", "bf16"))
         self.rollout.set_dynamics_ensemble(env.models)
         self.rollout.set_normalization(**env.norm)
         self.env_spec = env.spec

@@ -69,7 +69,8 @@ def train(variant, snapshot_dir=None, sampler_n_envs=None, sweep_iters=None, dev
     fit.set_ensemble([models[k] for k in mine])
     nn_env = NeuralNetEnv(name, models, default_norm(S, A), sam_mode=pop.get("sam_mode", "step_rand"),
                           reset_sampler=lambda n: np.asarray([real_env.reset() for _ in range(n)], np.float32),
-                          hidden=hidden[0], device=device, policy_hidden=tuple(params["policy"]["hidden_layers"]))
+                          hidden=hidden[0], device=device, policy_hidden=tuple(params["policy"]["hidden_layers"]),
+                          precision=dm.get("rollout_precision", "bf16"))      # extra key: "fp32" = reference arithmetic
     policy = GaussianMLPPolicy(S, A, tuple(params["policy"]["hidden_layers"]), init_std=pop["trpo"]["init_std"],
                                output_tanh=(params["policy"].get("output_nonlinearity") == "tf.tanh"),
                                device=device, seed=seed)
