@@ -120,6 +120,10 @@ int metrpo_rollout_set_policy(metrpo_rollout_t* h, const float* const* W, const 
 /* VecSimpleEnv.reset() with explicit states (env_helpers.py:585-595): states[B,S] become the
  * current observations, ts = 0.  The reference draws them from the real simulator. */
 int metrpo_rollout_reset(metrpo_rollout_t* h, const float* states, void* stream);
+/* Overwrite the states of `n` rows (device int32 row indices, device states [n,S]) WITHOUT touching
+ * their step counters: how the step-granular socket hands the done rows the simulator resets it
+ * drew in row order after a step (VecSimpleEnv.reset(dones), env_helpers.py:585-595). */
+int metrpo_rollout_set_rows(metrpo_rollout_t* h, const int32_t* rows, int n, const float* states, void* stream);
 
 /* VecSimpleEnv.step (env_helpers.py:597-607), socket B1.  actions[B,A] are the sampler's
  * UNCLIPPED actions; the kernel clips to [-1,1] (:599), evaluates all K models (:612-615),

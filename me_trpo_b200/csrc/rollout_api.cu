@@ -97,6 +97,14 @@ __global__ void reset_rows_kernel(const float* __restrict__ states, float* __res
   if (i < rows_padded) { row_ts[i] = 0; row_nreset[i] = 0; }
 }
 
+__global__ void set_rows_kernel(const int* __restrict__ rows, int n, const float* __restrict__ states,
+                                float* __restrict__ row_state, int B, int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * S) return;
+  const int r = rows[i / S];
+  if (r >= 0 && r < B) row_state[static_cast<size_t>(r) * S + i % S] = states[i];
+}
+
 }  // namespace metrpo
 
 using namespace metrpo;
@@ -485,6 +493,18 @@ extern "C" int metrpo_rollout_reset(metrpo_rollout_t* h, const float* states, vo
                                                      h->cfg.n_envs, h->cfg.state_dim, rows_pad);
   METRPO_CUDA_OK(cudaGetLastError());
   h->state_set = true;
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_rollout_set_rows(metrpo_rollout_t* h, const int32_t* rows, int n, const float* states,
+                                       void* stream_) {
+  if (!h || (n > 0 && (!rows || !states))) return set_error(METRPO_ERR_INVALID, "set_rows: null argument");
+  if (!h->state_set) return set_error(METRPO_ERR_STATE, "set_rows: call reset() first");
+  if (n <= 0) return METRPO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int S = h->cfg.state_dim;
+  set_rows_kernel<<<(n * S + 255) / 256, 256, 0, st>>>(rows, n, states, h->row_state, h->cfg.n_envs, S);
+  METRPO_CUDA_OK(cudaGetLastError());
   return METRPO_OK;
 }
 

@@ -95,9 +95,13 @@ class VecSimpleEnv:
         dones = np.asarray(dones, dtype=bool)
         n = int(dones.sum())
         if n:
-            fresh = torch.as_tensor(np.asarray(self.env.reset_sampler(n), np.float32), device=self.device)
+            rows = np.nonzero(dones)[0]
+            fresh_np = np.empty((n, self.env.S), np.float32)
+            for j, i in enumerate(rows):      # row order, simulator reset then model draw (:590-593)
+                fresh_np[j] = np.asarray(self.env.reset_sampler(1), np.float32)[0]
+                self.cur_model_idx[i] = self.rng.randint(self.env.n_models)
+            fresh = torch.as_tensor(fresh_np, device=self.device)
             self._obs[torch.as_tensor(dones, device=self.device)] = fresh
-            self.cur_model_idx[dones] = self.rng.randint(self.env.n_models, size=n)   # :593
             if dones.all():
                 self.rollout.reset(self._obs)      # ts = 0 for every row
                 self._needs_reset = False
@@ -118,13 +122,20 @@ class VecSimpleEnv:
         elif mode == "eps_rand":
             model_idx = self.cur_model_idx                              # :621-622
         std_noise = self.rng.normal(size=(B, self.env.S)).astype(np.float32) if mode == "model_mean_std" else None
-        reset_states = np.asarray(self.env.reset_sampler(B), np.float32)   # row i is used iff it finishes
-        obs, rew, done = self.rollout.step(actions, reset_states, model_idx=model_idx, std_noise=std_noise)
+        # the kernel needs a reset state per row that may finish; the REAL resets are drawn below
+        # for the done rows only, in row order, like the reference's reset(dones) loop (:590-593)
+        obs, rew, done = self.rollout.step(actions, self._obs, model_idx=model_idx, std_noise=std_noise)
         self.rollout.synchronize()
-        self._obs = obs
         done_np = done.cpu().numpy().astype(bool)
         if done_np.any():
-            self.cur_model_idx[done_np] = self.rng.randint(K, size=int(done_np.sum()))
+            rows = np.nonzero(done_np)[0]
+            fresh = np.empty((len(rows), self.env.S), np.float32)
+            for j, i in enumerate(rows):                                # :590-593
+                fresh[j] = np.asarray(self.env.reset_sampler(1), np.float32)[0]
+                self.cur_model_idx[i] = self.rng.randint(K)
+            self.rollout.set_rows(rows, fresh)
+            obs[torch.as_tensor(rows, device=obs.device, dtype=torch.long)] = torch.as_tensor(fresh, device=obs.device)
+        self._obs = obs
         return obs.cpu().numpy(), rew.cpu().numpy(), done_np, dict()
 
     def terminate(self):

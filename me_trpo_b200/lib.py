@@ -65,6 +65,7 @@ _PROTOS = {
     "metrpo_rollout_set_normalization": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "metrpo_rollout_set_policy": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp]),
     "metrpo_rollout_reset": (_i, [_vp, _vp, _vp]),
+    "metrpo_rollout_set_rows": (_i, [_vp, _vp, _i, _vp, _vp]),
     "metrpo_rollout_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "metrpo_rollout_run": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _u64, _u64, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

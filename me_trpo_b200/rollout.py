@@ -122,6 +122,17 @@ class EnsembleRollout:
         _lib.check(self._lib.metrpo_rollout_reset(self._h, _lib.ptr(st), _lib.stream_ptr(device=self.device)), "reset")
         self._keep.append(st)
 
+    def set_rows(self, rows, states):
+        """Overwrite the states of the given rows (step counters untouched): the done rows' fresh
+        simulator resets of the step-granular socket."""
+        dev = self.device
+        idx = torch.as_tensor(rows, dtype=torch.int32).to(dev).contiguous()
+        st = _f32(states, dev)
+        assert st.dim() == 2 and st.shape[0] == idx.numel() and st.shape[1] == self.S
+        _lib.check(self._lib.metrpo_rollout_set_rows(self._h, _lib.ptr(idx), int(idx.numel()), _lib.ptr(st),
+                                                     _lib.stream_ptr(device=self.device)), "set_rows")
+        self._keep = self._keep[-8:] + [(idx, st)]
+
     def step(self, actions, reset_states, model_idx=None, std_noise=None, seed=0, offset=0):
         dev = self.device
         act = _f32(actions, dev)
@@ -168,6 +179,31 @@ class EnsembleRollout:
             _lib.ptr(sn), int(seed), int(offset), 1 if determ else 0, g("obs"), g("act"), g("mean"),
             g("rew"), g("done"), _lib.ptr(out["final_states"]), _lib.stream_ptr(device=self.device)), "run")
         self._keep = self._keep[-8:] + [(init, pool, ep, mi, sn)]
+        return out
+
+    def run_continue(self, n_steps, reset_pool, eps=None, model_idx=None, std_noise=None, seed=0, offset=0,
+                     determ=False, out=None, want=("obs", "act", "mean", "rew", "done")):
+        """metrpo_rollout_continue: n_steps more steps from the row state the previous call left
+        (states, step counters, reset counts); `offset` = noise-stream index of its first step."""
+        dev, T, B, S, A = self.device, int(n_steps), self.B, self.S, self.A
+        pool = _f32(reset_pool, dev)
+        ep = None if eps is None else _f32(eps, dev)
+        mi = None if model_idx is None else torch.as_tensor(model_idx, dtype=torch.int32).to(dev).contiguous()
+        sn = None if std_noise is None else _f32(std_noise, dev)
+        out = {} if out is None else out
+        shapes = dict(obs=(T, B, S), act=(T, B, A), mean=(T, B, A), rew=(T, B), done=(T, B))
+        for name in want:
+            if name not in out:
+                out[name] = torch.empty(shapes[name], dtype=torch.uint8 if name == "done" else torch.float32, device=dev)
+            assert out[name].is_contiguous() and tuple(out[name].shape) == shapes[name]
+        if "final_states" not in out:
+            out["final_states"] = torch.empty(B, S, device=dev)
+        g = lambda n: _lib.ptr(out.get(n)) if n in want else None
+        _lib.check(self._lib.metrpo_rollout_continue(
+            self._h, T, _lib.ptr(pool), int(pool.shape[0]), _lib.ptr(ep), _lib.ptr(mi), _lib.ptr(sn), int(seed),
+            int(offset), 1 if determ else 0, g("obs"), g("act"), g("mean"), g("rew"), g("done"),
+            _lib.ptr(out["final_states"]), _lib.stream_ptr(device=self.device)), "continue")
+        self._keep = self._keep[-8:] + [(pool, ep, mi, sn)]
         return out
 
     def run_to_host(self, n_steps, init_states, reset_pool, host_out=None, dev_out=None, n_chunks=8,

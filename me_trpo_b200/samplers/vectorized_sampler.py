@@ -71,6 +71,8 @@ class VectorizedSampler(BaseSampler):
         algo, env = self.algo, self.algo.env
         B = self._n_envs
         n_resets = -(-T // algo.max_path_length)
+        if self._early_termination():
+            n_resets *= 4         # paths may end long before the timeout: more simulator resets per row
         R = int(self.reset_pool_size or B * n_resets)
         ctx = self.dist_ctx
         if ctx is None or not ctx.distributed or ctx.rank == 0:      # only rank 0 touches the simulator
@@ -85,14 +87,33 @@ class VectorizedSampler(BaseSampler):
             init = init[self._lo:self._hi]
         return init, pool
 
+    @staticmethod
+    def completed_samples_per_step(done):
+        """cum[t] = number of samples in paths COMPLETED by the end of step t (the `n_samples` of
+        samplers/vectorized_sampler.py:96-104), from the time-major done flags [T,B] (device)."""
+        T, B = done.shape
+        d = done.bool()
+        t_idx = torch.arange(T, device=done.device, dtype=torch.int64)[:, None].expand(T, B)
+        last = torch.cummax(torch.where(d, t_idx, torch.full_like(t_idx, -1)), dim=0).values   # last done <= t
+        prev = torch.cat([torch.full((1, B), -1, dtype=torch.int64, device=done.device), last[:-1]], 0)
+        length = torch.where(d, t_idx - prev, torch.zeros_like(t_idx))                         # path length at its end
+        return torch.cumsum(length.sum(dim=1), dim=0)
+
+    def _early_termination(self):
+        """Envs whose is_done ends paths before the timeout (only Ant defines is_done;
+        env_helpers.py:537): the number of steps the reference loop takes then depends on the data."""
+        return self.algo.env.env_name == "ant"
+
     def obtain_samples_flat(self, itr, determ=False, n_steps=None, check=True):
         """Time-major device buffers of one batch (this rank's rows).  `check` waits for the kernel
         and raises if it aborted on an internal wait timeout (the buffers would be partially
         written); pass False only if the caller checks `self.rollout.synchronize()` itself before
         consuming them."""
-        pol = self.algo.policy
+        pol, algo = self.algo.policy, self.algo
         T = int(n_steps or self._steps_for_batch())
         self.rollout.set_policy(pol.W, pol.b, pol.log_std)
+        if n_steps is None and self._early_termination():
+            return self._obtain_until_batch_size(T, determ)
         init, pool = self._start_states(T)
         out = self.rollout.run(T, init, pool, seed=self.seed, offset=self._calls * (1 << 20),
                                determ=determ)
@@ -101,12 +122,62 @@ class VectorizedSampler(BaseSampler):
             self.rollout.synchronize()
         return out
 
+    def _obtain_until_batch_size(self, T, determ):
+        """The reference's stop rule for early-terminating paths (`while n_samples < batch_size`,
+        samplers/vectorized_sampler.py:60,96-105): the loop ends after the first step at which the
+        COMPLETED paths hold batch_size samples.  With paths ending before the timeout that step
+        is not a multiple of the horizon and is not known in advance: the kernel runs in chunks
+        (metrpo_rollout_continue) until the count is reached and the buffers are cut there; paths
+        still open at that step are dropped by process_samples_flat's validity mask, like the
+        reference drops its running_paths."""
+        algo = self.algo
+        T_max = int(algo.max_path_length)
+        cap = T + 4 * T_max
+        B = self._hi - self._lo
+        dev = self.rollout.device
+        S, A = self.rollout.S, self.rollout.A
+        init, pool = self._start_states(cap)
+        full = dict(obs=torch.empty(cap, B, S, device=dev), act=torch.empty(cap, B, A, device=dev),
+                    mean=torch.empty(cap, B, A, device=dev), rew=torch.empty(cap, B, device=dev),
+                    done=torch.empty(cap, B, dtype=torch.uint8, device=dev))
+        base = self._calls * (1 << 20)
+        self._calls += 1
+        t0, chunk, final = 0, T, None
+        while True:
+            view = {k: v[t0:t0 + chunk] for k, v in full.items()}
+            if t0 == 0:
+                res = self.rollout.run(chunk, init, pool, seed=self.seed, offset=base, determ=determ, out=view)
+            else:
+                res = self.rollout.run_continue(chunk, pool, seed=self.seed, offset=base + t0, determ=determ, out=view)
+            self.rollout.synchronize()
+            final = res["final_states"]
+            t0 += chunk
+            cum = self.completed_samples_per_step(full["done"][:t0])
+            ctx = self.dist_ctx
+            if ctx is not None and ctx.distributed:          # n_samples counts the paths of ALL ranks
+                import torch.distributed as dist
+                dist.all_reduce(cum, group=ctx.group)
+            hit = torch.nonzero(cum >= int(algo.batch_size))
+            if hit.numel():
+                t_stop = int(hit[0].item()) + 1
+                break
+            if t0 + T_max > cap:
+                raise RuntimeError("obtain_samples: batch_size not reached within %d steps" % cap)
+            chunk = T_max
+        out = {k: v[:t_stop] for k, v in full.items()}
+        out["final_states"] = final
+        return out
+
     def obtain_samples(self, itr, determ=False):
         """The reference's contract (list of completed path dicts on the HOST).  The device->host
         copy of the trajectory is overlapped with the rollout itself (EnsembleRollout.run_to_host)."""
         pol = self.algo.policy
         T = int(self._steps_for_batch())
         self.rollout.set_policy(pol.W, pol.b, pol.log_std)
+        if self._early_termination():     # data-dependent number of steps (reference stop rule)
+            flat = self._obtain_until_batch_size(T, determ)
+            log_std = self.algo.policy.log_std.clamp(min=float(np.log(1e-6))).cpu().numpy()
+            return paths_from_flat({k: v.cpu().numpy() for k, v in flat.items()}, log_std)
         init, pool = self._start_states(T)
         host, self._dev_out = self.rollout.run_to_host(T, init, pool, seed=self.seed,
                                                        offset=self._calls * (1 << 20), determ=determ,

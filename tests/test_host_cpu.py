@@ -287,3 +287,22 @@ def test_dist_context_and_sharded_sampler_gloo(tmp_path):
         for n in range(n_res):
             for j in (0, nb - 1):
                 np.testing.assert_array_equal(r[i]["pool0"][(n * nb + j) % len(r[i]["pool0"])], pool[(n * B + lo + j) % len(pool)])
+
+
+def test_completed_samples_per_step_counts_like_the_reference_loop():
+    """n_samples of samplers/vectorized_sampler.py:96-104 (samples of COMPLETED paths after each
+    step) from time-major done flags, against a brute-force replay of the per-env bookkeeping."""
+    torch = pytest.importorskip("torch")
+    from me_trpo_b200.samplers.vectorized_sampler import VectorizedSampler
+    rs = np.random.RandomState(0)
+    done = (rs.rand(57, 23) < 0.07)
+    done[19] |= rs.rand(23) < 0.5
+    cum = VectorizedSampler.completed_samples_per_step(torch.tensor(done.astype(np.uint8))).numpy()
+    n, start, ref = 0, np.zeros(23, int), []
+    for t in range(57):
+        for b in range(23):
+            if done[t, b]:
+                n += t + 1 - start[b]
+                start[b] = t + 1
+        ref.append(n)
+    np.testing.assert_array_equal(cum, ref)

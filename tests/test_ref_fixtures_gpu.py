@@ -218,3 +218,45 @@ def test_cuda_trpo_half_matches_reference_iteration(env, K, seed):
             assert abs(kl - float(g[kk])) <= 2e-5
         prev_coeffs = g["baseline_coeffs"]
     pu.close()
+
+
+class _OrderedPool:
+    """The real simulator's reset(): hands out the reference's recorded reset states in call order."""
+
+    def __init__(self, pool):
+        self.pool, self.i = pool, 0
+
+    def __call__(self, n):
+        out = self.pool[self.i:self.i + n]
+        self.i += n
+        assert len(out) == n, "more simulator resets than the reference made"
+        return out
+
+
+@pytest.mark.parametrize("env,K,seed", VEC_CASES)
+@pytest.mark.parametrize("sam_mode", RI.SAM_MODES)
+def test_vec_env_socket_reproduces_reference_run_end_to_end(env, K, seed, sam_mode):
+    """The B1 socket (me_trpo_b200.env_helpers.NeuralNetEnv / VecSimpleEnv over libmetrpo.so, fp32
+    fidelity mode) driven exactly like the reference drove its own VecSimpleEnv when the fixture was
+    recorded: same global NumPy seed, same actions, the simulator's reset states in call order.  The
+    whole open-loop run -- model draws, timeouts, Ant's early terminations, which row received
+    which reset state -- must come out the same: the socket consumes np.random and the simulator
+    in the reference's order (env_helpers.py:583,590-593,619,626)."""
+    from me_trpo_b200.env_helpers import NeuralNetEnv
+    f = fx("D_vec__%s__%s__" % (env, sam_mode))
+    K_, B, T, mpl, seed_ = [int(v) for v in f["cfg"]]
+    _, _, S, A, _ = RI.ENVS[env]
+    models = RI.dynamics_weights(seed, S, A, RI.DROP[env], HID, K)
+    sim = _OrderedPool(f["pool"])
+    nn_env = NeuralNetEnv(env, models, _norm(f), sam_mode=sam_mode, reset_sampler=sim, hidden=HID[0],
+                          precision="fp32")
+    np.random.seed(seed_)
+    ve = nn_env.vec_env_executor(n_envs=B, max_path_length=mpl)
+    obs0 = ve.reset()
+    np.testing.assert_array_equal(obs0, f["obs0"].astype(np.float32))
+    for t in range(T):
+        o, r, d, info = ve.step(f["actions"][t].astype(np.float32))
+        np.testing.assert_array_equal(d, f["dones"][t])
+        assert np.abs(o - f["states"][t]).max() <= 1e-4 and np.abs(r - f["rewards"][t]).max() <= 2e-4
+        assert sim.i == int(f["n_reset_calls"][t])          # same number of simulator resets so far
+    ve.terminate()

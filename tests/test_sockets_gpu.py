@@ -122,3 +122,45 @@ def test_sampler_socket_returns_reference_style_paths():
     assert smp2._n_envs == 100
     smp2.shutdown_worker()
     smp.shutdown_worker()
+
+
+def test_ant_sampler_follows_reference_stop_rule():
+    """Early-terminating paths (Ant): obtain_samples stops after the first step at which the COMPLETED
+    paths hold batch_size samples (samplers/vectorized_sampler.py:60,96-105) -- not after a fixed
+    number of horizons.  fp32 mode, so that done thresholds match the fp32 oracle exactly."""
+    from me_trpo_b200.env_helpers import NeuralNetEnv
+    from me_trpo_b200.policies import GaussianMLPPolicy
+    from me_trpo_b200.samplers.vectorized_sampler import VectorizedSampler
+    env, K, B, T_max, hidden, batch = "ant", 3, 40, 12, 256, 1000
+    inp = mg.make_inputs(env, K, B, 4, hidden)
+    rs = np.random.RandomState(3)
+    big_pool = rs.normal(0, 0.1, (4000, 29)).astype(np.float32)
+    big_pool[:, 2] = rs.uniform(0.22, 0.98, size=4000)            # start inside the healthy band, some near the edge
+    nn_env = NeuralNetEnv(env, inp["models"], inp["norm"], reset_sampler=_PoolSampler(big_pool), hidden=hidden,
+                          precision="fp32")
+    pol = GaussianMLPPolicy(29, 8, (32, 32), device="cuda", seed=2)
+    algo = _Algo()
+    algo.env, algo.policy, algo.batch_size, algo.max_path_length = nn_env, pol, batch, T_max
+    smp = VectorizedSampler(algo, n_envs=B, seed=11)
+    smp.start_worker()
+    paths = smp.obtain_samples(0)
+    # oracle: the reference loop with the same Philox streams, per-row pool rule, fp32 arithmetic
+    W = [w.cpu().numpy() for w in pol.W]; b = [v.cpu().numpy() for v in pol.b]
+    opol = dict(W=W, b=b, log_std=pol.log_std.cpu().numpy())
+    T_fixed = -(-batch // (B * T_max)) * T_max
+    cap = T_fixed + 4 * T_max
+    n_res = -(-cap // T_max) * 4
+    init, pool = big_pool[:B], big_pool[B:B + B * n_res]
+    spec = oe.ENV_SPECS[env]
+    ve = orl.VecSimpleEnvOracle(env, inp["models"], inp["norm"], B, T_max, "step_rand", orl.PhiloxNoise(11, 0, 0, "step_rand"),
+                                pool, spec["S"], spec["A"], spec["drop"], reset_mode="per_row")
+    with np.errstate(invalid="ignore"):
+        ref = orl.obtain_samples(ve, opol, init, batch)
+    assert ve.t % T_max != 0 or len(ref) != B * (ve.t // T_max), "case must contain early terminations"
+    assert len(paths) == len(ref)
+    assert sum(len(p["rewards"]) for p in paths) == sum(len(p["rewards"]) for p in ref) >= batch
+    for a, r in zip(paths, ref):
+        assert len(a["rewards"]) == len(r["rewards"])
+        np.testing.assert_allclose(a["observations"], r["observations"], atol=5e-5)
+        np.testing.assert_allclose(a["rewards"], r["rewards"], atol=5e-5)
+    smp.shutdown_worker()
