@@ -229,6 +229,19 @@ typedef int (*metrpo_allreduce_fn)(void* user, double* dev_buf, int n, void* str
 int metrpo_trpo_create(const metrpo_trpo_cfg* cfg, metrpo_trpo_t** out);
 int metrpo_trpo_destroy(metrpo_trpo_t* h);
 int metrpo_trpo_set_allreduce(metrpo_trpo_t* h, metrpo_allreduce_fn fn, void* user);
+/* In-library all-reduce over NVLink / NVSwitch peer memory (one process per GPU on ONE node): every
+ * rank exposes a small exchange buffer through CUDA IPC; a reduction is then ONE launch of a one-shot
+ * kernel -- publish the local accumulator, flag the peers (system-scope release), wait for their
+ * flags, sum all ranks' copies with peer loads in rank order (bitwise identical result on every
+ * rank) -- instead of a host callback into NCCL per reduction.
+ *   metrpo_trpo_p2p_handle  allocates the exchange buffer and writes its 64-byte IPC handle (host)
+ *   metrpo_trpo_enable_p2p  handles: world x 64 bytes in rank order (gathered by the host framework);
+ *                           takes precedence over a callback set with metrpo_trpo_set_allreduce
+ * Every rank must issue the same sequence of trpo calls (they do: the update's control flow does
+ * not depend on data). */
+#define METRPO_IPC_HANDLE_BYTES 64
+int metrpo_trpo_p2p_handle(metrpo_trpo_t* h, void* handle_out);
+int metrpo_trpo_enable_p2p(metrpo_trpo_t* h, int rank, int world, const void* handles);
 /* Implementation of the per-sample pass (loss / gradient / Fisher-vector product):
  *   AUTO    the fastest measured one for the shape: the register-tiled fp32 pass (csrc/trpo_tiled.cuh)
  *           for policies whose layers are all <= 32 wide (every shipped params/*.json but

@@ -773,6 +773,61 @@ __global__ void __launch_bounds__(128) baseline_solve_kernel(const double* __res
 // =============================================================================================
 // C ABI
 // =============================================================================================
+// One-shot all-reduce over peer memory.  Exchange buffer of a rank: data[2][P2P_NMAX] doubles
+// (double-buffered by the parity of the reduction's sequence number) + flags[P2P_MAX_RANKS].
+// ---------------------------------------------------------------------------------------------
+namespace metrpo {
+constexpr int P2P_MAX_RANKS = 16;
+constexpr int P2P_NMAX = 16384;
+constexpr size_t P2P_BYTES = 2 * static_cast<size_t>(P2P_NMAX) * 8 + P2P_MAX_RANKS * 4 + 64;
+struct P2PArgs {
+  double* data[P2P_MAX_RANKS];
+  unsigned* flags[P2P_MAX_RANKS];
+  int rank, world;
+};
+__device__ __forceinline__ unsigned long long p2p_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256) k_allreduce_p2p(const P2PArgs a, double* __restrict__ buf, int n, unsigned seq) {
+  double* mine = a.data[a.rank] + static_cast<size_t>(seq & 1u) * P2P_NMAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = buf[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < a.world) {
+    // tell peer `threadIdx.x` that this rank's copy of reduction `seq` is complete ...
+    st_release_sys(a.flags[threadIdx.x] + a.rank, seq + 1u);
+    // ... and wait until that peer's copy is (bounded: a lost rank traps instead of hanging the GPU)
+    const unsigned long long t0 = p2p_timer_ns();
+    unsigned spins = 0;
+    while (ld_acquire_sys(a.flags[a.rank] + threadIdx.x) < seq + 1u) {
+      if ((++spins & 0x3ff) == 0 && p2p_timer_ns() - t0 > 10000000000ull) __trap();
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < a.world; ++w)      // rank order: the same sum, bit for bit, on every rank
+      s += ld_relaxed_sys_f64(a.data[w] + static_cast<size_t>(seq & 1u) * P2P_NMAX + i);
+    buf[i] = s;
+  }
+}
+}  // namespace metrpo
+
 using namespace metrpo;
 
 struct metrpo_trpo {
@@ -792,12 +847,20 @@ struct metrpo_trpo {
   double* adv_raw = nullptr;
   metrpo_allreduce_fn ar = nullptr;
   void* ar_user = nullptr;
+  // one-shot peer-memory all-reduce (metrpo_trpo_enable_p2p)
+  void* p2p_local = nullptr;              // this rank's exchange buffer (cudaMalloc, IPC-exported)
+  void* p2p_peer[P2P_MAX_RANKS] = {};     // every rank's buffer as mapped here (own entry = p2p_local)
+  int p2p_rank = 0, p2p_world = 0;
+  unsigned p2p_seq = 0;
   int last_launches = 0;
   int pass_impl = METRPO_TRPO_PASS_AUTO;
 };
 
 static void trpo_free(metrpo_trpo* h) {
   if (!h) return;
+  for (int w = 0; w < h->p2p_world; ++w)
+    if (w != h->p2p_rank && h->p2p_peer[w]) cudaIpcCloseMemHandle(h->p2p_peer[w]);
+  cudaFree(h->p2p_local);
   cudaFree(h->acc); cudaFree(h->cg); cudaFree(h->vec_f); cudaFree(h->trial_f); cudaFree(h->flags);
   cudaFree(h->gram); cudaFree(h->pos); cudaFree(h->base); cudaFree(h->adv_raw);
   delete h;
@@ -906,7 +969,56 @@ static int ensure_workspace(metrpo_trpo* h, long long N) {
   return METRPO_OK;
 }
 
+extern "C" int metrpo_trpo_p2p_handle(metrpo_trpo_t* h, void* handle_out) {
+  if (!h || !handle_out) return set_error(METRPO_ERR_INVALID, "trpo_p2p_handle: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == METRPO_IPC_HANDLE_BYTES, "IPC handle size");
+  METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
+  if (!h->p2p_local) {
+    METRPO_CUDA_OK(cudaMalloc(&h->p2p_local, P2P_BYTES));
+    METRPO_CUDA_OK(cudaMemset(h->p2p_local, 0, P2P_BYTES));
+  }
+  cudaIpcMemHandle_t hd;
+  METRPO_CUDA_OK(cudaIpcGetMemHandle(&hd, h->p2p_local));
+  std::memcpy(handle_out, &hd, sizeof(hd));
+  return METRPO_OK;
+}
+
+extern "C" int metrpo_trpo_enable_p2p(metrpo_trpo_t* h, int rank, int world, const void* handles) {
+  if (!h || !handles) return set_error(METRPO_ERR_INVALID, "trpo_enable_p2p: null argument");
+  if (world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world)
+    return set_error(METRPO_ERR_INVALID, "trpo_enable_p2p: need 0 <= rank < world <= %d", P2P_MAX_RANKS);
+  if (!h->p2p_local) return set_error(METRPO_ERR_STATE, "trpo_enable_p2p: call metrpo_trpo_p2p_handle first");
+  METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
+  for (int w = 0; w < world; ++w) {
+    if (w == rank) { h->p2p_peer[w] = h->p2p_local; continue; }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, static_cast<const char*>(handles) + static_cast<size_t>(w) * sizeof(hd), sizeof(hd));
+    const cudaError_t e = cudaIpcOpenMemHandle(&h->p2p_peer[w], hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int v = 0; v < w; ++v)
+        if (v != rank && h->p2p_peer[v]) { cudaIpcCloseMemHandle(h->p2p_peer[v]); h->p2p_peer[v] = nullptr; }
+      cudaGetLastError();
+      return set_error(METRPO_ERR_CUDA, "trpo_enable_p2p: cannot map rank %d's buffer: %s", w, cudaGetErrorString(e));
+    }
+  }
+  h->p2p_rank = rank; h->p2p_world = world; h->p2p_seq = 0;
+  return METRPO_OK;
+}
+
 static int allreduce(metrpo_trpo* h, double* buf, int n, cudaStream_t st) {
+  if (h->p2p_world > 1) {
+    if (n > P2P_NMAX) return set_error(METRPO_ERR_UNSUPPORTED, "all-reduce of %d doubles exceeds the exchange buffer", n);
+    P2PArgs a;
+    for (int w = 0; w < h->p2p_world; ++w) {
+      a.data[w] = static_cast<double*>(h->p2p_peer[w]);
+      a.flags[w] = reinterpret_cast<unsigned*>(static_cast<char*>(h->p2p_peer[w]) + 2 * static_cast<size_t>(P2P_NMAX) * 8);
+    }
+    a.rank = h->p2p_rank; a.world = h->p2p_world;
+    k_allreduce_p2p<<<1, 256, 0, st>>>(a, buf, n, h->p2p_seq++);
+    METRPO_CUDA_OK(cudaGetLastError());
+    ++h->last_launches;
+    return METRPO_OK;
+  }
   if (!h->ar) return METRPO_OK;
   const int rc = h->ar(h->ar_user, buf, n, st);
   if (rc != 0) return set_error(METRPO_ERR_STATE, "all-reduce callback failed (%d)", rc);

@@ -81,6 +81,8 @@ _PROTOS = {
     "metrpo_trpo_create": (_i, [ctypes.POINTER(TrpoCfg), ctypes.POINTER(_vp)]),
     "metrpo_trpo_destroy": (_i, [_vp]),
     "metrpo_trpo_set_allreduce": (_i, [_vp, ALLREDUCE_FN, _vp]),
+    "metrpo_trpo_p2p_handle": (_i, [_vp, _vp]),
+    "metrpo_trpo_enable_p2p": (_i, [_vp, _i, _i, _vp]),
     "metrpo_trpo_num_params": (_i, [_vp]),
     "metrpo_trpo_set_pass_impl": (_i, [_vp, _i]),
     "metrpo_trpo_last_launches": (_i, [_vp]),

@@ -33,6 +33,7 @@ class PolicyUpdate:
         _lib.check(self._lib.metrpo_trpo_create(ctypes.byref(cfg), ctypes.byref(self._h)), "metrpo_trpo_create")
         self.P = int(self._lib.metrpo_trpo_num_params(self._h))
         self._cb = None
+        self.allreduce_mode = None      # None (single GPU) | "p2p" | "nccl"
         self._keep = []
 
     def close(self):
@@ -53,12 +54,28 @@ class PolicyUpdate:
                    "trpo_set_pass_impl")
 
     # -- multi-GPU: sum the (tiny) accumulators across ranks with torch.distributed -------------
-    def enable_allreduce(self, group=None):
-        """Registers an all-reduce callback: every reduction of the update (gradient, each
-        Fisher-vector product, (loss, kl) pairs, advantage moments, baseline normal equations) is
-        summed over the process group.  Rows are sharded across ranks."""
+    def enable_allreduce(self, group=None, mode="auto"):
+        """Every reduction of the update (gradient, each Fisher-vector product, (loss, kl) pairs,
+        advantage moments, baseline normal equations) is summed over the process group; rows are
+        sharded across ranks.
+
+        mode "p2p": the library's own one-shot all-reduce over NVLink peer memory (one small kernel
+        per reduction, exchange buffers mapped through CUDA IPC; single node, summed in rank order so
+        that every rank gets the bit-identical result); "nccl": a host callback into
+        torch.distributed per reduction; "auto": p2p when the peer buffers can be mapped, else nccl."""
         import torch.distributed as dist
         dev = self.device
+        if mode in ("auto", "p2p"):
+            ok = self._enable_p2p(group)
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # all ranks or none
+            if int(flag.item()) == 1:
+                self.allreduce_mode = "p2p"
+                return
+            if mode == "p2p":
+                raise RuntimeError("peer-memory all-reduce unavailable: %s" % _lib.last_error())
+            self._lib.metrpo_trpo_enable_p2p(self._h, 0, 1, ctypes.create_string_buffer(64))   # back to world 1
+        self.allreduce_mode = "nccl"
 
         def _ar(user, buf, n, stream):
             try:
@@ -71,13 +88,28 @@ class PolicyUpdate:
         self._cb = _lib.ALLREDUCE_FN(_ar)
         _lib.check(self._lib.metrpo_trpo_set_allreduce(self._h, self._cb, None), "set_allreduce")
 
+    def _enable_p2p(self, group):
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = ctypes.create_string_buffer(64)
+        if self._lib.metrpo_trpo_p2p_handle(self._h, mine) != 0:
+            handles = [None] * world
+            dist.all_gather_object(handles, None, group=group)
+            return False
+        handles = [None] * world
+        dist.all_gather_object(handles, mine.raw, group=group)
+        if any(hd is None for hd in handles):
+            return False
+        blob = ctypes.create_string_buffer(b"".join(handles), 64 * world)
+        return self._lib.metrpo_trpo_enable_p2p(self._h, rank, world, blob) == 0
+
     # -- R10 ------------------------------------------------------------------------------------
     def process(self, obs, rew, done, baseline_coeffs=None, discount=1.0, gae_lambda=1.0,
                 center_adv=True, positive_adv=False):
         """obs[T,B,S], rew[T,B], done[T,B] (uint8) device tensors -> dict(adv, ret, valid, stats)."""
         T, B = rew.shape
         dev = self.device
-        if positive_adv and self._cb is not None:
+        if positive_adv and self.allreduce_mode is not None:
             # the shift needs the GLOBAL minimum; the accumulator all-reduce is a sum
             raise NotImplementedError("positive_adv with row-sharded samples (sum all-reduce only); "
                                       "the reference's TRPO path never sets it (algos/batch_polopt.py:33)")

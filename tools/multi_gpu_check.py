@@ -35,10 +35,11 @@ def rollout(rows_lo, rows_hi):
     return ro, out
 
 
-def update(out, allreduce):
+def update(out, allreduce, mode="auto", reps=1):
     pu = PolicyUpdate([spec["S"], 32, 32, spec["A"]], device=dev)
     if allreduce:
-        pu.enable_allreduce()
+        pu.enable_allreduce(mode=mode)
+        modes_used.append(pu.allreduce_mode)
     pr = pu.process(out["obs"], out["rew"], out["done"], discount=0.99)
     coeffs = pu.fit_baseline(out["obs"], pr["ret"], pr["valid"], out["done"])
     pr = pu.process(out["obs"], out["rew"], out["done"], baseline_coeffs=coeffs, discount=0.99)
@@ -48,10 +49,31 @@ def update(out, allreduce):
     parts.append(pol["log_std"])
     theta = torch.tensor(np.concatenate(parts).astype(np.float32), device=dev)
     N = out["rew"].numel()
+    ls = torch.tensor(pol["log_std"], device=dev)
+    theta0 = theta.clone()
     info = pu.update(theta, out["obs"].reshape(N, -1), out["act"].reshape(N, -1), pr["adv"].reshape(N),
-                     out["mean"].reshape(N, -1), torch.tensor(pol["log_std"], device=dev), valid=pr["valid"].reshape(N))
+                     out["mean"].reshape(N, -1), ls, valid=pr["valid"].reshape(N))
     torch.cuda.synchronize()
+    if reps > 1:      # timing of the whole update (device events, max over ranks)
+        ms = []
+        for _ in range(reps):
+            th = theta0.clone()
+            if allreduce:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pu.update(th, out["obs"].reshape(N, -1), out["act"].reshape(N, -1), pr["adv"].reshape(N),
+                      out["mean"].reshape(N, -1), ls, valid=pr["valid"].reshape(N))
+            e1.record(); torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        t = torch.tensor([min(ms)], device=dev, dtype=torch.float64)
+        if allreduce:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        timings.append(float(t.item()))
     return theta.cpu().numpy(), info.cpu().numpy(), coeffs.cpu().numpy()
+
+modes_used, timings = [], []
 
 ro_s, out_s = rollout(lo, hi)
 res = {}
@@ -63,7 +85,8 @@ if rank == 0:
     ro_f, out_f = rollout(0, B)
     res["rollout_bitexact"] = bool(torch.equal(torch.cat(gathered, 1), out_f["obs"]))
 # 2. sharded TRPO update with NCCL all-reduce vs single-GPU update on everything
-theta_s, info_s, coeffs_s = update(out_s, True)
+theta_n, info_n, coeffs_n = update(out_s, True, mode="nccl", reps=5)       # host callback into NCCL per reduction
+theta_s, info_s, coeffs_s = update(out_s, True, mode="p2p", reps=5)        # in-library one-shot NVLink all-reduce
 all_theta = [torch.empty(len(theta_s), device=dev) for _ in range(world)]
 dist.all_gather(all_theta, torch.tensor(theta_s, device=dev))
 if rank == 0:
@@ -75,6 +98,10 @@ if rank == 0:
     res["accepted"] = [float(info_s[4]), float(info_f[4])]
     res["mean_kl"] = [float(info_s[2]), float(info_f[2])]
     res["world_size"] = world
+    res["allreduce_modes"] = modes_used
+    res["update_ms_nccl_callback"], res["update_ms_p2p"] = timings[0], timings[1]
+    res["theta_max_abs_diff_p2p_vs_nccl"] = float(np.max(np.abs(theta_s - theta_n)))
+    res["samples_per_rank"] = int(out_s["rew"].numel())
     ok = (res["rollout_bitexact"] and res["theta_identical_across_ranks"]
           and res["theta_max_abs_diff_vs_single_gpu"] <= 1e-5 * max(1.0, res["theta_step_norm"]))
     res["ok"] = bool(ok)
