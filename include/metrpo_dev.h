@@ -29,6 +29,15 @@ int metrpo_bench_mma(int ts_mode, int N, int reps, int two_acc, int a_col, int d
  * clock64 span of warp 0. */
 int metrpo_bench_mma_sync(int kind, int warps, int reps, unsigned long long* out_dev, void* stream);
 
+/* Dev hook: the ensemble fit's batched TF32 tcgen05 GEMM (csrc/fit_gemm.cuh) on caller-provided
+ * device arrays.  C[m,n] = epi(sum_k A(m,k) B(n,k)) per model; a_mn / b_mn = 1: operand stored
+ * [k][m] / [k][n]; epi 0 plain, 1 relu(acc + bias[n]), 2 aux > 0 ? acc : 0. */
+int metrpo_dev_gemm_tf32(int M, int N, int Kd, int models, const float* A, long long lda,
+                         long long strideA, int a_mn, const float* B, long long ldb,
+                         long long strideB, int b_mn, float* C, long long ldc, long long strideC,
+                         int epi, const float* bias, long long strideBias, const float* aux,
+                         long long ldaux, long long strideAux, float* dbg_stage, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

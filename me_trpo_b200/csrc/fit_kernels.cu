@@ -9,13 +9,15 @@
 //                     :973-981) + per-model best-weights snapshot (:998-1007), all on the device
 //   metrpo_fit_restore_best   recover_weights (:876-879, :1034)
 //
-// The three GEMM shapes per layer and direction (forward, dgrad, wgrad; 1000 x 1024 x 1024 for the
-// big layer) are plain dense GEMMs and go to cuBLAS (strided-batched over the K models, TF32
-// tensor cores with fp32 accumulate by default, or true fp32); everything between them is
-// hand-written and fused: gather+normalise+column-drop, bias+ReLU, the MSE backward (bias b2,
-// de-normalisation, residual, loss reduction, dO and db2 in one pass), ReLU-mask + bias-gradient
-// column sums, and one Adam kernel over the K x P flat parameter block.  All of these are HBM
-// bound; DESIGN.md lists their bytes per element.
+// Default (METRPO_FIT_TF32): every contraction behind layer 0 -- forward, dgrad and wgrad of the
+// hidden and output layers, and the layer-0 weight gradient -- runs on the tcgen05 tensor cores
+// through ONE hand-written batched TF32 GEMM kernel (fit_gemm.cuh; TMA-fed, K-/MN-major operands
+// read in place, bias + ReLU or ReLU mask + bias-gradient column sums fused into the epilogue);
+// layer 0 itself (Din <= 88 deep) is fused into the gather kernel on the CUDA cores.  Around them:
+// the MSE backward (bias b2, de-normalisation, residual, loss reduction, dO and db2 in one pass)
+// and one Adam kernel over the K x P flat parameter block.  METRPO_FIT_FP32 is the fidelity mode:
+// true fp32 products through cuBLAS (bit-compatible with the oracle to 1e-7) with separate
+// bias / mask kernels.
 #include <cublas_v2.h>
 
 #include <cmath>
@@ -24,6 +26,7 @@
 
 #include "common.cuh"
 #include "philox.cuh"
+#include "fit_gemm.cuh"
 
 namespace metrpo {
 
@@ -31,7 +34,9 @@ constexpr uint32_t PHILOX_STREAM_FIT = 0x30000u;   // minibatch row indices
 
 struct FitDims {
   int S, A, SA, drop, Din, H, K;
-  int oW0, ob0, oW1, ob1, oW2, ob2, P;   // float offsets inside one model's parameter block
+  int rnd;                               // 1 (TF32 mode): producers round GEMM operands to TF32-nearest
+  int Sp, Dp;                            // S and Din rounded up to 32: row pitch of W2 / O and of Z (zero padded)
+  int oW0, ob0, oW1, ob1, oW2, ob2, P;   // float offsets inside one model's parameter block (W2 is [H][Sp])
 };
 
 // x_data[n][SA] (state, action), y_data[n][S] (next state).  Row r of model k's minibatch is sample
@@ -55,12 +60,15 @@ __global__ void fit_gather_kernel(FitDims d, const float* __restrict__ x_data, c
   const float* yr = y_data + static_cast<size_t>(i) * d.S;
   const float* in_mean = norm;
   const float* in_std = norm + d.SA;
-  float* z = Z + k * strideZ + static_cast<size_t>(r) * d.Din;
+  float* z = Z + k * strideZ + static_cast<size_t>(r) * d.Dp;
   float* xs = XS + k * strideS + static_cast<size_t>(r) * d.S;
   float* y = Y + k * strideS + static_cast<size_t>(r) * d.S;
   for (int c = threadIdx.x; c < d.SA; c += blockDim.x) {
     const float v = xr[c];
-    if (c >= d.drop) z[c - d.drop] = __fdiv_rn(__fsub_rn(v, in_mean[c]), in_std[c]);   // training.py:228,146-154
+    if (c >= d.drop) {   // training.py:228,146-154
+      const float zv = __fdiv_rn(__fsub_rn(v, in_mean[c]), in_std[c]);
+      z[c - d.drop] = d.rnd ? round_tf32(zv) : zv;
+    }
     if (c < d.S) { xs[c] = v; y[c] = yr[c]; }
   }
 }
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(256) fit_layer0_kernel(FitDims d, const float*
       const float v = x_data[static_cast<size_t>(sIdx[rr]) * d.SA + c];
       zv = __fdiv_rn(__fsub_rn(v, in_mean[c]), in_std[c]);
       if (blockIdx.y == 0) {
-        if (c >= d.drop) Z[k * strideZ + static_cast<size_t>(r) * d.Din + c - d.drop] = zv;
+        if (c >= d.drop) Z[k * strideZ + static_cast<size_t>(r) * d.Dp + c - d.drop] = d.rnd ? round_tf32(zv) : zv;
         if (c < d.S) {
           XS[k * strideS + static_cast<size_t>(r) * d.S + c] = v;
           Y[k * strideS + static_cast<size_t>(r) * d.S + c] = y_data[static_cast<size_t>(sIdx[rr]) * d.S + c];
@@ -147,10 +155,15 @@ __global__ void __launch_bounds__(256) fit_layer0_kernel(FitDims d, const float*
     const int r = r0 + 4 * ty + a;
     if (r < rows) {
       float4* o = reinterpret_cast<float4*>(H0 + k * strideH + static_cast<size_t>(r) * d.H + c0 + 8 * tx);
-      o[0] = make_float4(fmaxf(acc[a][0] + bb0.x, 0.f), fmaxf(acc[a][1] + bb0.y, 0.f), fmaxf(acc[a][2] + bb0.z, 0.f),
-                         fmaxf(acc[a][3] + bb0.w, 0.f));
-      o[1] = make_float4(fmaxf(acc[a][4] + bb1.x, 0.f), fmaxf(acc[a][5] + bb1.y, 0.f), fmaxf(acc[a][6] + bb1.z, 0.f),
-                         fmaxf(acc[a][7] + bb1.w, 0.f));
+      float4 o0 = make_float4(fmaxf(acc[a][0] + bb0.x, 0.f), fmaxf(acc[a][1] + bb0.y, 0.f), fmaxf(acc[a][2] + bb0.z, 0.f),
+                              fmaxf(acc[a][3] + bb0.w, 0.f));
+      float4 o1 = make_float4(fmaxf(acc[a][4] + bb1.x, 0.f), fmaxf(acc[a][5] + bb1.y, 0.f), fmaxf(acc[a][6] + bb1.z, 0.f),
+                              fmaxf(acc[a][7] + bb1.w, 0.f));
+      if (d.rnd) {   // H0 is the A operand of the TF32 layer-1 GEMMs
+        o0 = make_float4(round_tf32(o0.x), round_tf32(o0.y), round_tf32(o0.z), round_tf32(o0.w));
+        o1 = make_float4(round_tf32(o1.x), round_tf32(o1.y), round_tf32(o1.z), round_tf32(o1.w));
+      }
+      o[0] = o0; o[1] = o1;
     }
   }
 }
@@ -180,7 +193,8 @@ __global__ void fit_bias_relu_kernel(float* __restrict__ Hbuf, const float* __re
 __global__ void fit_mse_kernel(FitDims d, float* __restrict__ O, const float* __restrict__ XS,
                                const float* __restrict__ Y, const float* __restrict__ theta,
                                const float* __restrict__ norm, int rows, double inv_rows, int backward,
-                               long long strideS, double* __restrict__ loss_acc, float* __restrict__ part2) {
+                               long long strideS, long long strideO, double* __restrict__ loss_acc,
+                               float* __restrict__ part2) {
   const int k = blockIdx.y;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const float* b2 = theta + static_cast<size_t>(k) * d.P + d.ob2;
@@ -191,17 +205,18 @@ __global__ void fit_mse_kernel(FitDims d, float* __restrict__ O, const float* __
   float db_local[2] = {0.f, 0.f};   // lane owns columns lane, lane + 32 (S <= 64)
   for (int r = blockIdx.x * wpb + wib; r < rows; r += gridDim.x * wpb) {
     const size_t base = k * strideS + static_cast<size_t>(r) * d.S;
+    const size_t obase = k * strideO + static_cast<size_t>(r) * d.Sp;   // O rows are Sp floats apart
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int s = lane + 32 * q;
       if (s < d.S) {
-        const float o = __fadd_rn(O[base + s], b2[s]);
+        const float o = __fadd_rn(O[obase + s], b2[s]);
         const float pred = __fadd_rn(__fadd_rn(dmean[s], __fmul_rn(dstd[s], o)), XS[base + s]);
         const float diff = __fsub_rn(pred, Y[base + s]);
         lsum += static_cast<double>(diff) * diff;
         if (backward) {
           const float g = static_cast<float>(2.0 * inv_rows) * dstd[s] * diff;
-          O[base + s] = g;
+          O[obase + s] = d.rnd ? round_tf32(g) : g;
           db_local[q] += g;
         }
       }
@@ -356,6 +371,7 @@ struct metrpo_fit {
   bool norm_set = false;
   std::vector<char> w_set;
   int last_launches = 0;
+  int nslab_max = 0;      // row slabs of the bias-gradient partial buffers
 };
 
 static void fit_free(metrpo_fit* h) {
@@ -400,8 +416,10 @@ extern "C" int metrpo_fit_create(const metrpo_fit_cfg* cfg, metrpo_fit_t** out) 
   d.H = c.hidden; d.K = c.n_models;
   // every sub-block starts on a float4 boundary (H % 32 == 0; W0 and W2 are padded up)
   auto up4 = [](int v) { return (v + 3) / 4 * 4; };
+  d.Sp = (d.S + 31) / 32 * 32; d.Dp = (d.Din + 31) / 32 * 32;
+  d.rnd = c.precision == METRPO_FIT_TF32 ? 1 : 0;
   d.oW0 = 0; d.ob0 = up4(d.Din * d.H); d.oW1 = d.ob0 + d.H; d.ob1 = d.oW1 + d.H * d.H;
-  d.oW2 = d.ob1 + d.H; d.ob2 = d.oW2 + up4(d.H * d.S); d.P = d.ob2 + up4(d.S);
+  d.oW2 = d.ob1 + d.H; d.ob2 = d.oW2 + d.H * d.Sp; d.P = d.ob2 + up4(d.S);
   h->P_pad = d.P;
   h->R = c.max_rows;
   h->compute = c.precision == METRPO_FIT_FP32 ? CUBLAS_COMPUTE_32F : CUBLAS_COMPUTE_32F_FAST_TF32;
@@ -414,11 +432,12 @@ extern "C" int metrpo_fit_create(const metrpo_fit_cfg* cfg, metrpo_fit_t** out) 
   const size_t PK = static_cast<size_t>(d.P) * d.K * 4, RK = static_cast<size_t>(h->R) * d.K * 4;
   alloc((void**)&h->theta, PK); alloc((void**)&h->grad, PK); alloc((void**)&h->m, PK);
   alloc((void**)&h->v, PK); alloc((void**)&h->best, PK);
-  alloc((void**)&h->Z, RK * d.Din); alloc((void**)&h->XS, RK * d.S); alloc((void**)&h->Y, RK * d.S);
+  alloc((void**)&h->Z, RK * d.Dp); alloc((void**)&h->XS, RK * d.S); alloc((void**)&h->Y, RK * d.S);
   alloc((void**)&h->H0, RK * d.H); alloc((void**)&h->H1, RK * d.H); alloc((void**)&h->D1, RK * d.H);
-  alloc((void**)&h->O, RK * d.S);
+  alloc((void**)&h->O, RK * d.Sp);
   alloc((void**)&h->norm, (2 * d.SA + 2 * d.S) * 4);
-  const size_t nslab_max = (h->R + COLSUM_ROWS - 1) / COLSUM_ROWS;
+  const size_t nslab_max = static_cast<size_t>((h->R + 255) / 256) * 8;   // 32-row slabs of the GEMM epilogue
+  h->nslab_max = static_cast<int>(nslab_max);
   alloc((void**)&h->part1, nslab_max * d.K * d.H * 4); alloc((void**)&h->part0, nslab_max * d.K * d.H * 4);
   alloc((void**)&h->part2, static_cast<size_t>(148) * d.K * d.S * 4);
   alloc((void**)&h->loss_acc, d.K * 8); alloc((void**)&h->min_losses, d.K * 4); alloc((void**)&h->flags, d.K);
@@ -460,6 +479,11 @@ static int fit_copy_weights(metrpo_fit* h, int k, float* const* user, bool to_li
   const int len[6] = {d.Din * d.H, d.H, d.H * d.H, d.H, d.H * d.S, d.S};
   float* base = block + static_cast<size_t>(k) * d.P;
   for (int i = 0; i < 6; ++i) {
+    if (i == 4) {   // W2 lives as [H][Sp] (zero padded columns) inside the block
+      if (to_lib) METRPO_CUDA_OK(cudaMemcpy2DAsync(base + off[i], d.Sp * 4, user[i], d.S * 4, d.S * 4, d.H, cudaMemcpyDeviceToDevice, st));
+      else METRPO_CUDA_OK(cudaMemcpy2DAsync(user[i], d.S * 4, base + off[i], d.Sp * 4, d.S * 4, d.H, cudaMemcpyDeviceToDevice, st));
+      continue;
+    }
     if (to_lib) METRPO_CUDA_OK(cudaMemcpyAsync(base + off[i], user[i], len[i] * 4, cudaMemcpyDeviceToDevice, st));
     else METRPO_CUDA_OK(cudaMemcpyAsync(user[i], base + off[i], len[i] * 4, cudaMemcpyDeviceToDevice, st));
   }
@@ -529,30 +553,70 @@ static int fit_check_ready(metrpo_fit* h, const char* who) {
   return METRPO_OK;
 }
 
+// C = epi(A B^T) on the tcgen05 GEMM (fit_gemm.cuh), batched over the K models
+static int own_gemm(metrpo_fit* h, int M, int N, int Kd, const float* A, long long lda, long long sA, int a_mn,
+                    int a_ext, const float* B, long long ldb, long long sB, int b_mn, int b_ext, float* C,
+                    long long ldc, long long sC, int epi, const float* bias, const float* aux, float* colsum,
+                    int trans_store, cudaStream_t st, int a_kext = 0, int b_kext = 0) {
+  GemmParams p;
+  p.M = M; p.N = N; p.Kd = Kd; p.a_mn = a_mn; p.b_mn = b_mn; p.epi = epi; p.trans_store = trans_store;
+  p.round_out = (epi != GEMM_EPI_PLAIN) ? 1 : 0;   // H1 / dH1 / dH0 feed later GEMMs
+  p.C = C; p.ldc = ldc; p.strideC = sC; p.bias = bias; p.strideBias = h->d.P; p.colsum = colsum;
+  GemmOperands o;
+  o.A = A; o.lda = lda; o.strideA = sA; o.a_ext = a_ext; o.a_kext = a_kext;
+  o.B = B; o.ldb = ldb; o.strideB = sB; o.b_ext = b_ext; o.b_kext = b_kext;
+  o.aux = aux; o.ldaux = h->d.H; o.strideAux = static_cast<long long>(h->R) * h->d.H;
+  const int r = fit_gemm_launch(p, o, h->d.K, st);
+  if (r) return set_error(METRPO_ERR_CUDA, "fit: tcgen05 GEMM set-up failed (code %d; M %d N %d K %d)", r, M, N, Kd);
+  return METRPO_OK;
+}
+
 // gather + forward of `rows` rows per model; leaves O = H1 W2 (bias b2 is added by fit_mse_kernel)
 static int fit_forward(metrpo_fit* h, const float* x, const float* y, int n_data, const int* idx, int identity,
                        int row0, unsigned long long seed, unsigned long long offset, int rows, cudaStream_t st,
                        int& launches) {
   const FitDims& d = h->d;
-  const long long R = h->R, sZ = R * d.Din, sS = R * d.S, sH = R * d.H, P = d.P;
+  const long long R = h->R, sZ = R * d.Dp, sS = R * d.S, sO = R * d.Sp, sH = R * d.H, P = d.P;
+  const bool own = h->cfg.precision == METRPO_FIT_TF32;
   const int eb = static_cast<int>(std::min<long long>((static_cast<long long>(rows) * d.H / 4 + 255) / 256, 1184));
+  int rc;
   if (d.H % L0_COLS == 0) {
     const size_t smem0 = (static_cast<size_t>((L0_ROWS * (d.Din + 1) + 3) & ~3) + static_cast<size_t>(d.Din) * L0_COLS) * 4;
     fit_layer0_kernel<<<dim3((rows + L0_ROWS - 1) / L0_ROWS, d.H / L0_COLS, d.K), 256, smem0, st>>>(
         d, x, y, n_data, idx, identity, row0, seed, offset, rows, h->norm, h->theta, h->Z, h->XS, h->Y, h->H0, sZ, sS, sH);
-    launches -= 2;
-  } else {   // hidden widths that are not a multiple of 128: gather, cuBLAS GEMM, bias + ReLU
+    launches += 1;
+  } else {   // hidden widths that are not a multiple of 128: gather, then layer 0 as a GEMM
     dim3 blk(32, 8), grd((rows + 7) / 8, d.K);
     fit_gather_kernel<<<grd, blk, 0, st>>>(d, x, y, n_data, idx, identity, row0, seed, offset, rows, h->norm,
                                           h->Z, h->XS, h->Y, sZ, sS);
-    METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.H, d.Din, h->Z, d.Din, sZ, h->theta + d.oW0, d.H, P, h->H0, d.H, sH));
-    fit_bias_relu_kernel<<<dim3(eb, d.K), 256, 0, st>>>(h->H0, h->theta, d.ob0, P, rows, d.H, sH);
+    if (own) {   // H0 = relu(Z W0 + b0): A = Z [rows][Dp] (zero padded), B = W0 [k = Din][n = H] MN-major
+      rc = own_gemm(h, rows, d.H, d.Dp, h->Z, d.Dp, sZ, 0, rows, h->theta + d.oW0, d.H, P, 1, d.H, h->H0, d.H, sH,
+                    GEMM_EPI_BIAS_RELU, h->theta + d.ob0, nullptr, nullptr, 0, st, 0, d.Din);
+      if (rc != METRPO_OK) return rc;
+      launches += 2;
+    } else {
+      METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.H, d.Din, h->Z, d.Dp, sZ, h->theta + d.oW0, d.H, P, h->H0, d.H, sH));
+      fit_bias_relu_kernel<<<dim3(eb, d.K), 256, 0, st>>>(h->H0, h->theta, d.ob0, P, rows, d.H, sH);
+      launches += 3;
+    }
   }
-  METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.H, d.H, h->H0, d.H, sH, h->theta + d.oW1, d.H, P, h->H1, d.H, sH));
-  fit_bias_relu_kernel<<<dim3(eb, d.K), 256, 0, st>>>(h->H1, h->theta, d.ob1, P, rows, d.H, sH);
-  METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.S, d.H, h->H1, d.H, sH, h->theta + d.oW2, d.S, P, h->O, d.S, sS));
+  if (own) {
+    // H1 = relu(H0 W1 + b1): A = H0 [rows][H] K-major, B = W1 [k][n] MN-major, bias + ReLU in the epilogue
+    rc = own_gemm(h, rows, d.H, d.H, h->H0, d.H, sH, 0, rows, h->theta + d.oW1, d.H, P, 1, d.H, h->H1, d.H, sH,
+                  GEMM_EPI_BIAS_RELU, h->theta + d.ob1, nullptr, nullptr, 0, st);
+    if (rc != METRPO_OK) return rc;
+    // O = H1 W2: B = W2 [k = H][n = Sp] MN-major (zero padded columns), 128-column tile
+    rc = own_gemm(h, rows, d.S, d.H, h->H1, d.H, sH, 0, rows, h->theta + d.oW2, d.Sp, P, 1, d.Sp, h->O, d.Sp, sO,
+                  GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 0, st);
+    if (rc != METRPO_OK) return rc;
+    launches += 2;
+  } else {
+    METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.H, d.H, h->H0, d.H, sH, h->theta + d.oW1, d.H, P, h->H1, d.H, sH));
+    fit_bias_relu_kernel<<<dim3(eb, d.K), 256, 0, st>>>(h->H1, h->theta, d.ob1, P, rows, d.H, sH);
+    METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.S, d.H, h->H1, d.H, sH, h->theta + d.oW2, d.Sp, P, h->O, d.Sp, sO));
+    launches += 3;
+  }
   METRPO_CUDA_OK(cudaGetLastError());
-  launches += 6;
   return METRPO_OK;
 }
 
@@ -566,28 +630,58 @@ extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, 
   if (rc != METRPO_OK) return rc;
   METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  METRPO_BLAS_OK(cublasSetStream(h->blas, st));
+  const bool own = h->cfg.precision == METRPO_FIT_TF32;
+  if (!own) METRPO_BLAS_OK(cublasSetStream(h->blas, st));
   const FitDims& d = h->d;
-  const long long R = h->R, sZ = R * d.Din, sS = R * d.S, sH = R * d.H, P = d.P;
+  const long long R = h->R, sZ = R * d.Dp, sS = R * d.S, sO = R * d.Sp, sH = R * d.H, P = d.P;
   int launches = 0;
   METRPO_CUDA_OK(cudaMemsetAsync(h->loss_acc, 0, d.K * 8, st));
   rc = fit_forward(h, x, y, n_data, idx, 0, 0, seed, offset, batch, st, launches);
   if (rc != METRPO_OK) return rc;
   const int mb = std::min((batch + 7) / 8, 148);
   fit_mse_kernel<<<dim3(mb, d.K), 256, 8 * d.S * 4, st>>>(d, h->O, h->XS, h->Y, h->theta, h->norm, batch, 1.0 / batch, 1,
-                                                     sS, h->loss_acc, h->part2);
-  // dW2[H,S] = H1^T dO;  dH1 = dO W2^T (masked by H1 > 0, db1 = column sums)
-  METRPO_BLAS_OK(gemm_rm(h, true, false, d.H, d.S, batch, h->H1, d.H, sH, h->O, d.S, sS, h->grad + d.oW2, d.S, P));
-  METRPO_BLAS_OK(gemm_rm(h, false, true, batch, d.H, d.S, h->O, d.S, sS, h->theta + d.oW2, d.S, P, h->D1, d.H, sH));
-  fit_relu_bwd_colsum_kernel<<<dim3(d.H / 32, (batch + COLSUM_ROWS - 1) / COLSUM_ROWS, d.K), dim3(8, 32), 0, st>>>(h->D1, h->H1, batch, d.H, sH, h->part1);
-  // dW1 = H0^T dH1;  dH0 = dH1 W1^T -> H1's buffer (H1 is dead now), masked by H0 > 0, db0
-  METRPO_BLAS_OK(gemm_rm(h, true, false, d.H, d.H, batch, h->H0, d.H, sH, h->D1, d.H, sH, h->grad + d.oW1, d.H, P));
-  METRPO_BLAS_OK(gemm_rm(h, false, true, batch, d.H, d.H, h->D1, d.H, sH, h->theta + d.oW1, d.H, P, h->H1, d.H, sH));
-  fit_relu_bwd_colsum_kernel<<<dim3(d.H / 32, (batch + COLSUM_ROWS - 1) / COLSUM_ROWS, d.K), dim3(8, 32), 0, st>>>(h->H1, h->H0, batch, d.H, sH, h->part0);
-  // dW0[Din,H] = Z^T dH0
-  METRPO_BLAS_OK(gemm_rm(h, true, false, d.Din, d.H, batch, h->Z, d.Din, sZ, h->H1, d.H, sH, h->grad + d.oW0, d.H, P));
+                                                     sS, sO, h->loss_acc, h->part2);
+  int nslab;
+  if (own) {
+    nslab = fit_gemm_colsum_slabs(batch, d.H);
+    // dW2[H,S] = H1^T dO: A = H1 [k = row][m] MN-major, B = dO [k = row][n = Sp] MN-major
+    rc = own_gemm(h, d.H, d.S, batch, h->H1, d.H, sH, 1, d.H, h->O, d.Sp, sO, 1, d.Sp, h->grad + d.oW2, d.Sp, P,
+                  GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 0, st);
+    if (rc != METRPO_OK) return rc;
+    // dH1 = (dO W2^T) * (H1 > 0), db1 = column sums: A = dO [rows][Sp] K-major, B = W2 [n = H][k = Sp] K-major
+    rc = own_gemm(h, batch, d.H, d.Sp, h->O, d.Sp, sO, 0, batch, h->theta + d.oW2, d.Sp, P, 0, d.H, h->D1, d.H, sH,
+                  GEMM_EPI_MASK, nullptr, h->H1, h->part1, 0, st);
+    if (rc != METRPO_OK) return rc;
+    // dW1 = H0^T dH1: both operands MN-major, reduction over the rows
+    rc = own_gemm(h, d.H, d.H, batch, h->H0, d.H, sH, 1, d.H, h->D1, d.H, sH, 1, d.H, h->grad + d.oW1, d.H, P,
+                  GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 0, st);
+    if (rc != METRPO_OK) return rc;
+    // dH0 = (dH1 W1^T) * (H0 > 0) -> H1's buffer (H1 is dead now), db0 = column sums: both operands K-major
+    rc = own_gemm(h, batch, d.H, d.H, h->D1, d.H, sH, 0, batch, h->theta + d.oW1, d.H, P, 0, d.H, h->H1, d.H, sH,
+                  GEMM_EPI_MASK, nullptr, h->H0, h->part0, 0, st);
+    if (rc != METRPO_OK) return rc;
+    // dW0[Din,H] = Z^T dH0, computed as its transpose (M = H fills the 128 tensor-core rows) and
+    // stored transposed: A = dH0 [k = row][m = H] MN-major, B = Z [k = row][n = Dp] MN-major
+    rc = own_gemm(h, d.H, d.Din, batch, h->H1, d.H, sH, 1, d.H, h->Z, d.Dp, sZ, 1, d.Dp, h->grad + d.oW0, d.H, P,
+                  GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 1, st);
+    if (rc != METRPO_OK) return rc;
+    launches += 5;
+  } else {
+    nslab = (batch + COLSUM_ROWS - 1) / COLSUM_ROWS;
+    // dW2[H,S] = H1^T dO;  dH1 = dO W2^T (masked by H1 > 0, db1 = column sums)
+    METRPO_BLAS_OK(gemm_rm(h, true, false, d.H, d.S, batch, h->H1, d.H, sH, h->O, d.Sp, sO, h->grad + d.oW2, d.Sp, P));
+    METRPO_BLAS_OK(gemm_rm(h, false, true, batch, d.H, d.S, h->O, d.Sp, sO, h->theta + d.oW2, d.Sp, P, h->D1, d.H, sH));
+    fit_relu_bwd_colsum_kernel<<<dim3(d.H / 32, nslab, d.K), dim3(8, 32), 0, st>>>(h->D1, h->H1, batch, d.H, sH, h->part1);
+    // dW1 = H0^T dH1;  dH0 = dH1 W1^T -> H1's buffer (H1 is dead now), masked by H0 > 0, db0
+    METRPO_BLAS_OK(gemm_rm(h, true, false, d.H, d.H, batch, h->H0, d.H, sH, h->D1, d.H, sH, h->grad + d.oW1, d.H, P));
+    METRPO_BLAS_OK(gemm_rm(h, false, true, batch, d.H, d.H, h->D1, d.H, sH, h->theta + d.oW1, d.H, P, h->H1, d.H, sH));
+    fit_relu_bwd_colsum_kernel<<<dim3(d.H / 32, nslab, d.K), dim3(8, 32), 0, st>>>(h->H1, h->H0, batch, d.H, sH, h->part0);
+    // dW0[Din,H] = Z^T dH0
+    METRPO_BLAS_OK(gemm_rm(h, true, false, d.Din, d.H, batch, h->Z, d.Dp, sZ, h->H1, d.H, sH, h->grad + d.oW0, d.H, P));
+    launches += 7;
+  }
   fit_bias_grad_finish_kernel<<<dim3((2 * d.H + d.S + 255) / 256, d.K), 256, 0, st>>>(
-      d, h->part1, h->part0, (batch + COLSUM_ROWS - 1) / COLSUM_ROWS, h->part2, mb, h->grad);
+      d, h->part1, h->part0, nslab, h->part2, mb, h->grad);
   // Adam (tf.train.AdamOptimizer defaults beta1 0.9, beta2 0.999, epsilon 1e-8)
   h->adam_t += 1;
   const double b1 = 0.9, b2 = 0.999;
@@ -595,7 +689,7 @@ extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, 
   const long long n4 = P * d.K / 4;
   fit_adam_kernel<<<static_cast<int>(std::min<long long>((n4 + 255) / 256, 148 * 8)), 256, 0, st>>>(
       h->theta, h->grad, h->m, h->v, n4, static_cast<float>(lr_t), 0.9f, 0.999f, 1e-8f);
-  launches += 10;
+  launches += 3;
   if (losses) { fit_losses_out_kernel<<<1, 64, 0, st>>>(h->loss_acc, losses, d.K); ++launches; }
   METRPO_CUDA_OK(cudaGetLastError());
   h->last_launches = launches;
@@ -612,9 +706,9 @@ extern "C" int metrpo_fit_eval(metrpo_fit_t* h, const float* x, const float* y, 
   if (rc != METRPO_OK) return rc;
   METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  METRPO_BLAS_OK(cublasSetStream(h->blas, st));
+  if (h->cfg.precision != METRPO_FIT_TF32) METRPO_BLAS_OK(cublasSetStream(h->blas, st));
   const FitDims& d = h->d;
-  const long long sS = static_cast<long long>(h->R) * d.S;
+  const long long sS = static_cast<long long>(h->R) * d.S, sO = static_cast<long long>(h->R) * d.Sp;
   int launches = 0;
   METRPO_CUDA_OK(cudaMemsetAsync(h->loss_acc, 0, d.K * 8, st));
   for (int row0 = 0; row0 < n; row0 += h->R) {
@@ -623,7 +717,7 @@ extern "C" int metrpo_fit_eval(metrpo_fit_t* h, const float* x, const float* y, 
     if (rc != METRPO_OK) return rc;
     const int mb = std::min((rows + 7) / 8, 148);
     fit_mse_kernel<<<dim3(mb, d.K), 256, 8 * d.S * 4, st>>>(d, h->O, h->XS, h->Y, h->theta, h->norm, rows, 1.0 / n, 0, sS,
-                                                       h->loss_acc, h->part2);
+                                                       sO, h->loss_acc, h->part2);
     ++launches;
   }
   fit_snapshot_flags_kernel<<<1, 64, 0, st>>>(h->loss_acc, h->min_losses, h->flags, losses, d.K, snapshot);

@@ -909,15 +909,15 @@ extern "C" int metrpo_rollout_set_trace(metrpo_rollout_t* h, int cta, int t0, in
   return set_error(METRPO_ERR_UNSUPPORTED, "set_trace: library was built without -DMETRPO_TRACE");
 #endif
   if (!h->trace) {
-    METRPO_CUDA_OK(cudaMalloc(&h->trace, 3 * TRACE_CAP * 8));
+    METRPO_CUDA_OK(cudaMalloc(&h->trace, 4 * TRACE_CAP * 8));
   }
-  METRPO_CUDA_OK(cudaMemset(h->trace, 0, 3 * TRACE_CAP * 8));
+  METRPO_CUDA_OK(cudaMemset(h->trace, 0, 4 * TRACE_CAP * 8));
   h->trace_cta = cta; h->trace_t0 = t0; h->trace_t1 = t1;
   return METRPO_OK;
 }
 extern "C" int metrpo_rollout_get_trace(metrpo_rollout_t* h, unsigned long long* out_host) {
   if (!h || !h->trace || !out_host) return set_error(METRPO_ERR_INVALID, "get_trace: no trace");
   METRPO_CUDA_OK(cudaDeviceSynchronize());
-  METRPO_CUDA_OK(cudaMemcpy(out_host, h->trace, 3 * TRACE_CAP * 8, cudaMemcpyDeviceToHost));
+  METRPO_CUDA_OK(cudaMemcpy(out_host, h->trace, 4 * TRACE_CAP * 8, cudaMemcpyDeviceToHost));
   return METRPO_OK;
 }

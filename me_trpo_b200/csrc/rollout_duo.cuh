@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
   const int total_ssteps = 2 * total_psteps;
 
   int st_dbg = 0;
+#ifdef METRPO_TRACE
+  bool tr_on = false;
+  int tr_n = 0;
+#endif
   if (tid == 0) {
     abort_smem = 0;
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars[D_FULL + i], 1); mbar_init(&bars[D_EMPTY + i], 1); }
@@ -295,6 +299,8 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
         const int sidx = u & 1;                                   // stream of this stream-step
         const uint32_t ztm = tmem + p.tm_z + sidx * zcols;        // A of L0: this stream's Z columns
         st_dbg = (u << 8) | 0xff;
+        TRACE_ON(lane == 0 && (u >> 1) >= p.trace_t0 && (u >> 1) < p.trace_t1);
+        TRACE(1, 0x1000 | sidx);
         // stream-step prologue: Z of this stream ready, W0 tile of the first group, acc0 drained
         DWAITW4(D_ZREADY + sidx, (u >> 1) & 1, D_W0FULL + (int)(gg & 1), (gg >> 1) & 1,
                 gg > 0 ? D_ACC0FREE : -1, (gg - 1) & 1, -1, 0);
@@ -307,11 +313,13 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
         }
         __syncwarp();
         ++gg;
+        TRACE(1, 0x1001);
         DWAITW4(D_FULL + (int)s, sphase, D_H0FULL + 0, hg & 1,
                 NGSp > 1 ? D_ACC0FREE : -1, (gg - 1) & 1, NGSp > 1 ? D_W0FULL + (int)(gg & 1) : -1, (gg >> 1) & 1);
         int gp = 0, ncl = 0;
         for (int G = 0; G < NGSp; ++G) {
           st_dbg = (u << 8) | (2 * G);
+          TRACE(1, 0x100 | G);
           const bool next_l0 = (G + 1 < NGSp);
           const bool first_of_pass = (gp == 0), last_of_pass = (gp == NG - 1);
           uint32_t s1 = s + 1, sphase1 = sphase;
@@ -365,8 +373,10 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
           if (last_of_pass) {
             // L2 of this pass: acc2 (+)= H1 (in place in acc1's columns) * W2 chunk.  The first L2
             // of a stream-step overwrites acc2: the OTHER stream's epilogue must have read it.
+            TRACE(1, 0x2000 | ncl);
             DWAITW4(D_H1FULL + 0, npass & 1, D_W2FULL, w2n & 1,
                     (ncl == 0 && u > 0) ? D_ACC2FREE : -1, (u - 1) & 1, -1, 0);
+            TRACE(1, 0x2100 | ncl);
             ++w2n;
 #pragma unroll 1
             for (int sub = 0; sub < nsl; ++sub) {
@@ -382,6 +392,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
             }
             if (elect_one()) umma_commit(&bars[D_W2EMPTY]);
             __syncwarp();
+            TRACE(1, 0x2200 | ncl);
             ++npass; ++ncl; gp = 0;
           } else {
             ++gp;
@@ -396,6 +407,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
         }
         if (elect_one()) umma_commit(&bars[D_ACC2FULL]);
         __syncwarp();
+        TRACE(1, 0x1002);
       }
 #undef DWAITW4
 #undef DPROBE4
@@ -464,6 +476,8 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
         for (int t = t0; t < t1; ++t, ++ps) {
           const uint32_t u = 2u * static_cast<uint32_t>(ps) + grp;   // ordinal of this stream-step
           st_dbg = (t << 8) | 0xf0;
+          TRACE_ON(e == 0 && ps >= p.trace_t0 && ps < p.trace_t1);
+          TRACE(2 + grp, 0x1000);
           // ================= begin step: action + Z operand =================
           if (!have_action) {
             // first step of a segment: every CTA runs the policy for all rows of the tile
@@ -547,9 +561,11 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&bars[D_ZREADY + grp]);
+          TRACE(2 + grp, 0x1001);
 
           // ================= this stream's MMA phase =================
           DWAITB(D_START + grp, (u >> 1) & 1);
+          TRACE(2 + grp, 0x1002);
           {
             const int NG = p.KC / 2;
             int egp = 0, enc = 0;
@@ -559,6 +575,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
               {
                 uint32_t v0[32], v1[32], pk[32];
                 DWAITB(D_ACC0FULL + (gg & 1), (gg >> 1) & 1);
+                TRACE(2 + grp, 0x100 | G);
                 tc_fence_after();
                 tmem_ld32(tmem + lane_base + p.tm_acc0, v0);
                 tmem_ld32(tmem + lane_base + p.tm_acc0 + 32, v1);
@@ -581,6 +598,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[D_H0FULL + 1]);
+                TRACE(2 + grp, 0x200 | G);
               }
               int drain_nc = -1;
               if (G == NGSp - 1) drain_nc = NCp - 1;
@@ -589,6 +607,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
               if (drain_nc >= 0) {
                 const uint32_t a1n = u * static_cast<uint32_t>(NCp) + drain_nc;   // global pass index
                 DWAITB(D_ACC1FULL, a1n & 1);
+                TRACE(2 + grp, 0x300 | drain_nc);
                 tc_fence_after();
                 uint32_t va0[32], va1[32], pk[32];
                 const uint32_t a1 = tmem + lane_base + TM_ACC1;
@@ -605,6 +624,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
                   tc_fence_before();
                   mbar_arrive(&bars[D_H1FULL + sub]);
                 }
+                TRACE(2 + grp, 0x400 | drain_nc);
               }
             }
           }
@@ -613,7 +633,9 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
           st_dbg = (t << 8) | 0xf1;
           float cand[SMAX];
           {
+            TRACE(2 + grp, 0x1003);
             DWAITB(D_ACC2FULL, u & 1);
+            TRACE(2 + grp, 0x1004);
             tc_fence_after();
             uint32_t v[32];
             tmem_ld32(tmem + lane_base + p.tm_acc2, v);
@@ -644,6 +666,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
                   v[s] = __float_as_uint(c == 0 ? __fadd_rn(mine_v, other) : __fadd_rn(other, mine_v));
                 }
             }
+            TRACE(2 + grp, 0x1005);
 #pragma unroll
             for (int s = 0; s < SMAX; ++s) {
               if (s < S) {
@@ -729,6 +752,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
               }
             }
             named_bar_sync(bar_id, EPI_THREADS);
+            TRACE(2 + grp, 0x1006);
             // ---- policy of step t+1 for this half's owned rows: 2 threads per row ----
             if (want_pol) {
               const int part = e & 1, jl = e >> 1;
@@ -813,6 +837,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
             }
             // ---- publish / meet the gang: one release + one acquire poll per warp ----
             named_bar_sync(bar_id, EPI_THREADS);   // policy threads of other warps wrote this warp's rows' records
+            TRACE(2 + grp, 0x1007);
             int okw = 1;
             unsigned* rc = dp.rctr + (slot * 2 + grp);
             if (lane == 0) red_release_gpu_add(rc, 1u);
@@ -830,6 +855,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
               okw = dwait_ge(rc, 4u * static_cast<unsigned>(K * cs) * (xn_cnt + 1), p.dbg, 101u, (uint32_t)st_dbg) ? 1 : 0;
             okw = __shfl_sync(0xffffffffu, okw, 0);
             if (!okw) goto bail;
+            TRACE(2 + grp, 0x1008);
             ++xn_cnt;
             float dnf = 0.f;
             if (valid) {
@@ -859,6 +885,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
               dnf = qd.x;
             }
             if (dnf != 0.f) { ts = 0; nreset += 1; } else { ts += 1; }
+            TRACE(2 + grp, 0x1009);
             have_action = want_pol;
           }
         }  // t

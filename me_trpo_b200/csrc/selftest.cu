@@ -6,6 +6,7 @@
 #include "metrpo.h"
 #include "metrpo_dev.h"
 #include "common.cuh"
+#include "fit_gemm.cuh"
 
 namespace metrpo {
 
@@ -165,5 +166,25 @@ extern "C" int metrpo_selftest_umma(int mode, int N, int K, int reps, const void
                                                  C, cycles);
   METRPO_CUDA_OK(cudaGetLastError());
   if (packed) METRPO_CUDA_OK(cudaFreeAsync(packed, stream));
+  return METRPO_OK;
+}
+
+// Dev hook: the fit's batched TF32 GEMM (fit_gemm.cuh) on caller-provided device arrays.
+extern "C" int metrpo_dev_gemm_tf32(int M, int N, int Kd, int models, const float* A, long long lda,
+                                    long long strideA, int a_mn, const float* B, long long ldb,
+                                    long long strideB, int b_mn, float* C, long long ldc, long long strideC,
+                                    int epi, const float* bias, long long strideBias, const float* aux,
+                                    long long ldaux, long long strideAux, float* dbg, void* stream_) {
+  (void)dbg;
+  GemmParams p;
+  p.M = M; p.N = N; p.Kd = Kd; p.a_mn = a_mn; p.b_mn = b_mn; p.epi = epi; p.trans_store = 0; p.round_out = 0;
+  p.C = C; p.ldc = ldc; p.strideC = strideC; p.bias = bias; p.strideBias = strideBias; p.colsum = nullptr;
+  GemmOperands o;
+  o.A = A; o.lda = lda; o.strideA = strideA; o.a_ext = M; o.a_kext = 0;
+  o.B = B; o.ldb = ldb; o.strideB = strideB; o.b_ext = N; o.b_kext = 0;
+  o.aux = aux; o.ldaux = ldaux; o.strideAux = strideAux;
+  const int r = fit_gemm_launch(p, o, models, static_cast<cudaStream_t>(stream_));
+  if (r) return set_error(METRPO_ERR_CUDA, "dev_gemm_tf32: launch set-up failed (%d)", r);
+  METRPO_CUDA_OK(cudaGetLastError());
   return METRPO_OK;
 }

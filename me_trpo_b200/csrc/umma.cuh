@@ -277,6 +277,14 @@ __device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(hi), "f"(lo));
   return v;
 }
+// fp32 -> nearest TF32 (10-bit mantissa, ties away), returned as fp32 with the low 13 bits clear.
+// tcgen05.mma.kind::tf32 TRUNCATES raw fp32 operands; producers that round their outputs remove the
+// systematic shrink (2^-11 mean relative per operand) the truncation would add.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);

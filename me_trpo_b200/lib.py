@@ -112,6 +112,8 @@ _DEV_PROTOS = {
     "metrpo_bench_mma": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "metrpo_bench_mma_sync": (_i, [_i, _i, _i, _vp, _vp]),
     "metrpo_selftest_umma": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "metrpo_dev_gemm_tf32": (_i, [_i, _i, _i, _i, _vp, _ll, _ll, _i, _vp, _ll, _ll, _i, _vp, _ll, _ll,
+                                  _i, _vp, _ll, _vp, _ll, _ll, _vp, _vp]),
 }
 
 _lib = None
