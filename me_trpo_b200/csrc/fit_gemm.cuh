@@ -31,16 +31,19 @@
 namespace metrpo {
 
 constexpr int GM_BK = 32;
-constexpr int GM_THREADS = 192;
+constexpr int GM_EPI_WARPS = 8;                     // two per TMEM lane quarter (even / odd chunks)
+constexpr int GM_THREADS = 64 + 32 * GM_EPI_WARPS;
 constexpr int GM_CHUNK_BYTES = 128 * 128;            // one 128-row x 32-column fp32 epilogue chunk
 template <int MT, int BN> struct GemmCfg {
   static constexpr int BM = 128 * MT;
   static constexpr int A_BYTES = BM * GM_BK * 4;     // 16 / 32 KB
   static constexpr int B_BYTES = BN * GM_BK * 4;     // 16 / 32 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (STAGE_BYTES > 49152) ? 3 : 4;
+  static constexpr int STAGES = (STAGE_BYTES > 49152) ? 3 : 6;   // 192 KB either way
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int NCH = BN / 32;                // epilogue chunks per 128-row sub-tile
+  static constexpr int NBUF = RING_BYTES / GM_CHUNK_BYTES;   // 16 KB staging buffers the idle ring provides
+  static constexpr int NHEAD = (MT == 1) ? 0 : (NBUF - NCH < NCH ? NBUF - NCH : NCH);   // sub-tile 1 chunks with a buffer of their own
   static constexpr int TMEM_COLS = MT * BN;
   static constexpr int SMEM_BYTES = RING_BYTES + BN * 4 + 256 + 1024;
   static_assert(NCH * GM_CHUNK_BYTES <= RING_BYTES, "epilogue staging must fit the stage ring");
@@ -54,8 +57,9 @@ struct GemmParams {
   int epi;
   int round_out;                // 1: round C to TF32-nearest (it is the operand of a later GEMM)
   int trans_store;              // 1: store C transposed, C[n * ldc + m], from registers (GEMM_EPI_PLAIN only)
-  float* C; long long ldc, strideC;                     // used by the transposed store only (else tmC)
+  float* C; long long ldc, strideC;                     // ldc % 4 == 0 unless trans_store
   const float* bias; long long strideBias;              // GEMM_EPI_BIAS_RELU: bias[n] per model
+  unsigned long long* dbg;      // dev: %globaltimer stamps of CTA (0,0,0): start | set-up done | accumulators full | stores issued | stores done
   float* colsum;                // GEMM_EPI_MASK, optional: per (model, 32-row slab) column sums of C,
                                 //   [model][gridDim.y * MT * 4][N] (summed in a fixed order by the caller)
 };
@@ -96,6 +100,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* 
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// at most N of this thread's most recent bulk groups still read their shared-memory source
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -118,11 +126,13 @@ fit_gemm_tf32_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + Cfg::STAGES;        // [STAGES]
   uint64_t* accfull = bars + 2 * Cfg::STAGES;
-  uint64_t* auxfull = accfull + 1;             // mask tile of the current 128-row sub-tile landed
-  uint64_t* subdone = accfull + 2;             // all four epilogue warps finished a sub-tile (4 arrivals)
+  uint64_t* auxfull = accfull + 1;             // [3] mask tiles landed: sub-tile 0 | head of sub-tile 1 | its tail
+  uint64_t* subdone = accfull + 4;             // all epilogue warps are done with sub-tile 0's buffers
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool dbg_on = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (dbg_on && tid == 64) p.dbg[0] = globaltimer_ns();
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * Cfg::BM, model = blockIdx.z;
   const int nkb = (p.Kd + GM_BK - 1) / GM_BK;
   const int nch = min(Cfg::NCH, (p.N - n0 + 31) / 32);   // chunks of this tile that hold real columns
@@ -130,8 +140,8 @@ fit_gemm_tf32_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA
   if (tid == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(accfull, 1);
-    mbar_init(auxfull, 1);
-    mbar_init(subdone, 4);
+    for (int i = 0; i < 3; ++i) mbar_init(&auxfull[i], 1);
+    mbar_init(subdone, GM_EPI_WARPS);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -143,6 +153,7 @@ fit_gemm_tf32_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (dbg_on && tid == 64) p.dbg[1] = globaltimer_ns();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -159,13 +170,26 @@ fit_gemm_tf32_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA
         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
       }
       if (p.epi == GEMM_EPI_MASK) {
-        // mask tiles of the epilogue go into the (now idle) stage ring, one 128-row sub-tile at a time
+        // mask tiles of the epilogue go into the (now idle) stage ring: sub-tile 0 -> buffers 0 .. NCH-1,
+        // the first NHEAD chunks of sub-tile 1 -> buffers NCH .., its remaining chunks reuse sub-tile
+        // 0's FIRST buffers (whose stores drain first) once all epilogue warps are done with them
         mbar_wait(accfull, 0);
-        for (int mt = 0; mt < MT; ++mt) {
-          if (mt > 0) mbar_wait(subdone, (mt - 1) & 1);
-          mbar_arrive_expect_tx(auxfull, nch * GM_CHUNK_BYTES);
-          for (int ch = 0; ch < nch; ++ch)
-            tma_load_4d(sStage + ch * GM_CHUNK_BYTES, &tmAux, n0 + ch * 32, m0 + mt * 128, 0, model, auxfull);
+        mbar_arrive_expect_tx(&auxfull[0], nch * GM_CHUNK_BYTES);
+        for (int ch = 0; ch < nch; ++ch)
+          tma_load_4d(sStage + ch * GM_CHUNK_BYTES, &tmAux, n0 + ch * 32, m0, 0, model, &auxfull[0]);
+        if (MT > 1) {
+          const int nhead = min(nch, Cfg::NHEAD);
+          if (nhead > 0) {
+            mbar_arrive_expect_tx(&auxfull[1], nhead * GM_CHUNK_BYTES);
+            for (int ch = 0; ch < nhead; ++ch)
+              tma_load_4d(sStage + (Cfg::NCH + ch) * GM_CHUNK_BYTES, &tmAux, n0 + ch * 32, m0 + 128, 0, model, &auxfull[1]);
+          }
+          if (nch > nhead) {
+            mbar_wait(subdone, 0);
+            mbar_arrive_expect_tx(&auxfull[2], (nch - nhead) * GM_CHUNK_BYTES);
+            for (int ch = nhead; ch < nch; ++ch)
+              tma_load_4d(sStage + (ch - nhead) * GM_CHUNK_BYTES, &tmAux, n0 + ch * 32, m0 + 128, 0, model, &auxfull[2]);
+          }
         }
       }
     }
@@ -200,90 +224,133 @@ fit_gemm_tf32_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA
   } else {
     // ---- epilogue: warp w reads TMEM lanes (w % 4) * 32 .. + 31 = rows of that quarter of a sub-tile ----
     const int q = warp & 3;
+    const int par = (warp - 2) >> 2;                 // this warp takes the chunks of this parity
     const float* biasm = p.bias ? p.bias + model * p.strideBias : nullptr;
     if (p.epi == GEMM_EPI_BIAS_RELU) {
-      for (int i = tid - 64; i < BN; i += 128) sBias[i] = (n0 + i < p.N) ? biasm[n0 + i] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = tid - 64; i < BN; i += 32 * GM_EPI_WARPS) sBias[i] = (n0 + i < p.N) ? biasm[n0 + i] : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * GM_EPI_WARPS) : "memory");
     }
     mbar_wait(accfull, 0);
     tc_fence_after();
+    if (dbg_on && tid == 64) p.dbg[2] = globaltimer_ns();
     const int rl = q * 32 + lane;                    // row inside the 128-row sub-tile
     const uint32_t sw = rl & 7;
-    for (int mt = 0; mt < MT; ++mt) {
-      const int mrow0 = m0 + mt * 128 + q * 32;
-      if (p.epi == GEMM_EPI_MASK) mbar_wait(auxfull, mt & 1);
-      float* csum = p.colsum ? p.colsum + (static_cast<size_t>(model) * gridDim.y * MT * 4 +
-                                           (blockIdx.y * MT + mt) * 4 + q) * p.N : nullptr;
-      for (int ch = 0; ch < nch; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + mt * BN + ch * 32, v);
-        tmem_ld_wait();
-        if (p.trans_store) {                   // thread = row m, register j = column: C[n][m], coalesced over lanes
-          float* Cm = p.C + model * p.strideC;
-          if (mrow0 + lane < p.M) {
+    const uint32_t tq = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    if (p.trans_store) {
+      // thread = row m, register j = column: C[n][m] straight from registers, coalesced over lanes
+      float* Cm = p.C + model * p.strideC;
+      for (int mt = 0; mt < MT; ++mt) {
+        const int m = m0 + mt * 128 + rl;
+        for (int ch = par; ch < nch; ch += 2) {
+          uint32_t v[32];
+          tmem_ld32(tq + mt * BN + ch * 32, v);
+          tmem_ld_wait();
+          if (m < p.M) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (n0 + ch * 32 + j < p.N) Cm[static_cast<size_t>(n0 + ch * 32 + j) * p.ldc + mrow0 + lane] = __uint_as_float(v[j]);
+              if (n0 + ch * 32 + j < p.N) Cm[static_cast<size_t>(n0 + ch * 32 + j) * p.ldc + m] = __uint_as_float(v[j]);
           }
-          continue;
         }
-        uint8_t* buf = sStage + ch * GM_CHUNK_BYTES;
-        uint8_t* rowp = buf + rl * 128;
-        if (p.epi == GEMM_EPI_MASK) {
+      }
+    } else {
+      // chunk groups: (sub-tile 0, all chunks) | (sub-tile 1, chunks with a buffer of their own) |
+      // (sub-tile 1, chunks that reuse sub-tile 0's buffers).  Per group: every chunk goes TMEM ->
+      // registers -> (mask | bias + ReLU) -> swizzled staging tile; then ONE proxy fence and one TMA
+      // store per chunk (this warp's 32-row slab), committed as one bulk group.
+      const int nhead = min(nch, Cfg::NHEAD);
+      const int ngroups = (MT == 1) ? 1 : 3;
+      for (int g = 0; g < ngroups; ++g) {
+        const int mt = g == 0 ? 0 : 1;
+        const int c_lo = g == 2 ? nhead : 0;
+        const int c_hi = g == 1 ? nhead : nch;
+        if (c_lo >= c_hi) continue;
+        const int boff = g == 1 ? Cfg::NCH : (g == 2 ? -nhead : 0);   // staging buffer of chunk ch = boff + ch
+        if (p.epi == GEMM_EPI_MASK) mbar_wait(&auxfull[g], 0);
+        else if (g == 2) {
+          // the buffers reused here are those of this warp's FIRST stores (one bulk group per chunk): on
+          // a full tile NHEAD / 2 of its NCH / 2 + NHEAD / 2 groups have to be done, the rest may be pending
+          if (lane == 0) {
+            if (nch == Cfg::NCH) bulk_wait_group_read<Cfg::NCH / 2>();
+            else bulk_wait_group_read0();
+          }
+          __syncwarp();
+        }
+
+        const int mrow0 = m0 + mt * 128 + q * 32;
+        const int c_first = c_lo + ((c_lo ^ par) & 1);   // first chunk of this warp's parity in the group
+        uint32_t va[32], vb[32];
+        if (c_first < c_hi) tmem_ld32(tq + mt * BN + c_first * 32, va);
+        for (int ch = c_first; ch < c_hi; ch += 2) {
+          tmem_ld_wait();
+          const bool odd = ((ch - c_first) >> 1) & 1;
+          // the next chunk's TMEM load is in flight while this one is transformed
+          if (ch + 2 < c_hi) {
+            if (odd) tmem_ld32(tq + mt * BN + (ch + 2) * 32, va);
+            else     tmem_ld32(tq + mt * BN + (ch + 2) * 32, vb);
+          }
+          uint8_t* rowp = sStage + (boff + ch) * GM_CHUNK_BYTES + rl * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float4 a = *reinterpret_cast<const float4*>(rowp + ((c ^ sw) << 4));
-            if (!(a.x > 0.f)) v[4 * c] = 0u;
-            if (!(a.y > 0.f)) v[4 * c + 1] = 0u;
-            if (!(a.z > 0.f)) v[4 * c + 2] = 0u;
-            if (!(a.w > 0.f)) v[4 * c + 3] = 0u;
-          }
-        } else if (p.epi == GEMM_EPI_BIAS_RELU) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 b = *reinterpret_cast<const float4*>(sBias + ch * 32 + 4 * c);
-            v[4 * c] = __float_as_uint(fmaxf(__uint_as_float(v[4 * c]) + b.x, 0.f));
-            v[4 * c + 1] = __float_as_uint(fmaxf(__uint_as_float(v[4 * c + 1]) + b.y, 0.f));
-            v[4 * c + 2] = __float_as_uint(fmaxf(__uint_as_float(v[4 * c + 2]) + b.z, 0.f));
-            v[4 * c + 3] = __float_as_uint(fmaxf(__uint_as_float(v[4 * c + 3]) + b.w, 0.f));
+            float x0 = __uint_as_float(odd ? vb[4 * c] : va[4 * c]), x1 = __uint_as_float(odd ? vb[4 * c + 1] : va[4 * c + 1]);
+            float x2 = __uint_as_float(odd ? vb[4 * c + 2] : va[4 * c + 2]), x3 = __uint_as_float(odd ? vb[4 * c + 3] : va[4 * c + 3]);
+            float4* slot = reinterpret_cast<float4*>(rowp + ((c ^ sw) << 4));
+            if (p.epi == GEMM_EPI_MASK) {
+              const float4 a = *slot;
+              x0 = a.x > 0.f ? x0 : 0.f; x1 = a.y > 0.f ? x1 : 0.f; x2 = a.z > 0.f ? x2 : 0.f; x3 = a.w > 0.f ? x3 : 0.f;
+            } else if (p.epi == GEMM_EPI_BIAS_RELU) {
+              const float4 b = *reinterpret_cast<const float4*>(sBias + ch * 32 + 4 * c);
+              x0 = fmaxf(x0 + b.x, 0.f); x1 = fmaxf(x1 + b.y, 0.f); x2 = fmaxf(x2 + b.z, 0.f); x3 = fmaxf(x3 + b.w, 0.f);
+            }
+            if (p.round_out) { x0 = round_tf32(x0); x1 = round_tf32(x1); x2 = round_tf32(x2); x3 = round_tf32(x3); }
+            *slot = make_float4(x0, x1, x2, x3);
           }
         }
-        if (p.round_out) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(round_tf32(__uint_as_float(v[j])));
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(rowp + ((c ^ sw) << 4)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         __syncwarp();
-        if (csum) {   // lane j sums column j over the warp's 32 rows (rows past M hold zeros)
-          float cs = 0.f;
-          const uint8_t* slab = buf + q * 4096;
+        if (dbg_on && tid == 64 && g == 0) p.dbg[6] = globaltimer_ns();
+        if (p.colsum) {   // lane j sums column j over the warp's 32 rows (rows past M hold zeros)
+          float* csum = p.colsum + (static_cast<size_t>(model) * gridDim.y * MT * 4 + (blockIdx.y * MT + mt) * 4 + q) * p.N;
+          for (int ch = c_first; ch < c_hi; ch += 2) {
+            const uint8_t* slab = sStage + (boff + ch) * GM_CHUNK_BYTES + q * 4096;
+            float cs0 = 0.f, cs1 = 0.f;
 #pragma unroll 8
-          for (int i = 0; i < 32; ++i)
-            cs += *reinterpret_cast<const float*>(slab + i * 128 + ((((lane >> 2) ^ i) & 7) << 4) + (lane & 3) * 4);
-          const int n = n0 + ch * 32 + lane;
-          if (n < p.N) csum[n] = cs;
+            for (int i = 0; i < 32; i += 2) {
+              cs0 += *reinterpret_cast<const float*>(slab + i * 128 + ((((lane >> 2) ^ i) & 7) << 4) + (lane & 3) * 4);
+              cs1 += *reinterpret_cast<const float*>(slab + (i + 1) * 128 + ((((lane >> 2) ^ (i + 1)) & 7) << 4) + (lane & 3) * 4);
+            }
+            const int n = n0 + ch * 32 + lane;
+            if (n < p.N) csum[n] = cs0 + cs1;
+          }
         }
+        if (dbg_on && tid == 64 && g == 0) p.dbg[7] = globaltimer_ns();
+        // staged slab -> global by TMA (32-row x 128 B boxes, clipped at M, N by the tensor map), one bulk
+        // group per chunk.  (Plain 128-bit stores of full lines were measured too: 6.9 us instead of
+        // 5.4 us per 256 x 256 tile -- either way the 80 CTAs write their 20 MB at the same time.)
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(&tmC, buf + q * 4096, n0 + ch * 32, mrow0, 0, model);
-          bulk_commit_group();
+          for (int ch = c_first; ch < c_hi; ch += 2) {
+            tma_store_4d(&tmC, sStage + (boff + ch) * GM_CHUNK_BYTES + q * 4096, n0 + ch * 32, mrow0, 0, model);
+            bulk_commit_group();
+          }
+          if (g == 0 && p.epi == GEMM_EPI_MASK && MT > 1 && nch > nhead) {
+            // the tail mask tiles of sub-tile 1 overwrite the first NCH - NHEAD buffers: this warp's
+            // first (NCH - NHEAD) / 2 stores must have been read
+            if (nch == Cfg::NCH) bulk_wait_group_read<Cfg::NCH / 2 - (Cfg::NCH - Cfg::NHEAD) / 2>();
+            else bulk_wait_group_read0();
+            mbar_arrive(subdone);
+          }
         }
-      }
-      if (MT > 1 && !p.trans_store && mt + 1 < MT) {
-        // the next sub-tile reuses the staging chunks: the bulk stores must have read them
-        if (lane == 0) bulk_wait_group_read0();
         __syncwarp();
-        if (p.epi == GEMM_EPI_MASK && lane == 0) mbar_arrive(subdone);
       }
+      if (dbg_on && tid == 64) p.dbg[3] = globaltimer_ns();
+      if (lane == 0) bulk_wait_group0();
+      if (dbg_on && tid == 64) p.dbg[4] = globaltimer_ns();
     }
-    if (lane == 0 && !p.trans_store) bulk_wait_group0();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_COLS);
+  if (dbg_on && tid == 64) p.dbg[5] = globaltimer_ns();
 }
 
 // ------------------------------- host side -------------------------------

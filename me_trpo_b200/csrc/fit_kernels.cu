@@ -112,21 +112,43 @@ __global__ void __launch_bounds__(256) fit_layer0_kernel(FitDims d, const float*
   __syncthreads();
   const float* in_mean = norm;
   const float* in_std = norm + d.SA;
-  for (int q = tid; q < L0_ROWS * d.SA; q += 256) {
-    const int rr = q / d.SA, c = q - rr * d.SA, r = r0 + rr;
-    float zv = 0.f;
-    if (r < rows) {
-      const float v = x_data[static_cast<size_t>(sIdx[rr]) * d.SA + c];
-      zv = __fdiv_rn(__fsub_rn(v, in_mean[c]), in_std[c]);
-      if (blockIdx.y == 0) {
-        if (c >= d.drop) Z[k * strideZ + static_cast<size_t>(r) * d.Dp + c - d.drop] = d.rnd ? round_tf32(zv) : zv;
-        if (c < d.S) {
-          XS[k * strideS + static_cast<size_t>(r) * d.S + c] = v;
-          Y[k * strideS + static_cast<size_t>(r) * d.S + c] = y_data[static_cast<size_t>(sIdx[rr]) * d.S + c];
+  // the scattered reads of up to 8 elements per thread are issued back to back (a store between two
+  // loads would serialise the DRAM latencies), then normalised and stored
+  const int total = L0_ROWS * d.SA;
+  for (int base = 0; base < total; base += 256 * 8) {
+    float xv[8], yv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int q = base + u * 256 + tid;
+      xv[u] = 0.f; yv[u] = 0.f;
+      if (q < total) {
+        const int rr = q / d.SA, c = q - rr * d.SA;
+        if (r0 + rr < rows) {
+          xv[u] = __ldg(&x_data[static_cast<size_t>(sIdx[rr]) * d.SA + c]);
+          if (blockIdx.y == 0 && c < d.S) yv[u] = __ldg(&y_data[static_cast<size_t>(sIdx[rr]) * d.S + c]);
         }
       }
     }
-    if (c >= d.drop) zs[rr * Dp + c - d.drop] = zv;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int q = base + u * 256 + tid;
+      if (q < total) {
+        const int rr = q / d.SA, c = q - rr * d.SA, r = r0 + rr;
+        float zv = 0.f;
+        if (r < rows) {
+          const float v = xv[u];
+          zv = __fdiv_rn(__fsub_rn(v, in_mean[c]), in_std[c]);
+          if (blockIdx.y == 0) {
+            if (c >= d.drop) Z[k * strideZ + static_cast<size_t>(r) * d.Dp + c - d.drop] = d.rnd ? round_tf32(zv) : zv;
+            if (c < d.S) {
+              XS[k * strideS + static_cast<size_t>(r) * d.S + c] = v;
+              Y[k * strideS + static_cast<size_t>(r) * d.S + c] = yv[u];
+            }
+          }
+        }
+        if (c >= d.drop) zs[rr * Dp + c - d.drop] = zv;
+      }
+    }
   }
   __syncthreads();
   const int ty = tid >> 4, tx = tid & 15;   // rows 4ty..4ty+3, columns 8tx..8tx+7
@@ -223,7 +245,14 @@ __global__ void fit_mse_kernel(FitDims d, float* __restrict__ O, const float* __
     }
   }
   for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-  if (lane == 0) atomicAdd(&loss_acc[k], lsum * inv_rows);
+  __shared__ double sh_loss[32];
+  if (lane == 0) sh_loss[wib] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {   // one atomic per block (the warps' sums are added in a fixed order first)
+    double t = 0.0;
+    for (int w = 0; w < wpb; ++w) t += sh_loss[w];
+    atomicAdd(&loss_acc[k], t * inv_rows);
+  }
   if (backward) {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -279,23 +308,33 @@ __global__ void fit_relu_bwd_colsum_kernel(float* __restrict__ dH, const float* 
   }
 }
 
-// db1, db0, db2 = fixed-order sums of the per-slab / per-block partials
-__global__ void fit_bias_grad_finish_kernel(FitDims d, const float* __restrict__ part1, const float* __restrict__ part0,
-                                            int nslab, const float* __restrict__ part2, int nblk2,
-                                            float* __restrict__ grad) {
-  const int k = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+// db1, db0, db2 = fixed-order sums of the per-slab / per-block partials.  Block = 32 columns x 8
+// slab groups: every thread sums its slabs (stride 8) in order, the 8 group sums are added in order.
+__global__ void __launch_bounds__(256) fit_bias_grad_finish_kernel(FitDims d, const float* __restrict__ part1,
+                                                                   const float* __restrict__ part0, int nslab,
+                                                                   const float* __restrict__ part2, int nblk2,
+                                                                   float* __restrict__ grad) {
+  __shared__ float red[8][33];
+  const int k = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
   float* g = grad + static_cast<size_t>(k) * d.P;
-  if (j < 2 * d.H) {
-    const float* p = (j < d.H ? part1 : part0) + static_cast<size_t>(k) * nslab * d.H + (j < d.H ? j : j - d.H);
-    float s = 0.f;
-    for (int b = 0; b < nslab; ++b) s += p[static_cast<size_t>(b) * d.H];
-    g[(j < d.H ? d.ob1 : d.ob0) + (j < d.H ? j : j - d.H)] = s;
-  } else if (j < 2 * d.H + d.S) {
-    const int c = j - 2 * d.H;
-    const float* p = part2 + static_cast<size_t>(k) * nblk2 * d.S + c;
-    float s = 0.f;
-    for (int b = 0; b < nblk2; ++b) s += p[static_cast<size_t>(b) * d.S];
-    g[d.ob2 + c] = s;
+  const float* p = nullptr;
+  int n = 0, stride = 0, out = -1;
+  if (j < d.H) { p = part1 + static_cast<size_t>(k) * nslab * d.H + j; n = nslab; stride = d.H; out = d.ob1 + j; }
+  else if (j < 2 * d.H) { p = part0 + static_cast<size_t>(k) * nslab * d.H + (j - d.H); n = nslab; stride = d.H; out = d.ob0 + j - d.H; }
+  else if (j < 2 * d.H + d.S) { p = part2 + static_cast<size_t>(k) * nblk2 * d.S + (j - 2 * d.H); n = nblk2; stride = d.S; out = d.ob2 + j - 2 * d.H; }
+  float s = 0.f;
+  if (p) {
+#pragma unroll 4
+    for (int b = ty; b < n; b += 8) s += p[static_cast<size_t>(b) * stride];
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && out >= 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][tx];
+    g[out] = t;
   }
 }
 
@@ -372,11 +411,16 @@ struct metrpo_fit {
   std::vector<char> w_set;
   int last_launches = 0;
   int nslab_max = 0;      // row slabs of the bias-gradient partial buffers
+  // backward pass: weight-gradient GEMMs run on a side stream next to the data-gradient GEMMs
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_w2 = nullptr, ev_d1 = nullptr, ev_join = nullptr;
 };
 
 static void fit_free(metrpo_fit* h) {
   if (!h) return;
   if (h->blas) cublasDestroy(h->blas);
+  if (h->side) cudaStreamDestroy(h->side);
+  for (cudaEvent_t e : {h->ev_fork, h->ev_w2, h->ev_d1, h->ev_join}) if (e) cudaEventDestroy(e);
   cudaFree(h->theta); cudaFree(h->grad); cudaFree(h->m); cudaFree(h->v); cudaFree(h->best);
   cudaFree(h->Z); cudaFree(h->XS); cudaFree(h->Y); cudaFree(h->H0); cudaFree(h->H1); cudaFree(h->O);
   cudaFree(h->D1); cudaFree(h->norm); cudaFree(h->part1); cudaFree(h->part0); cudaFree(h->part2); cudaFree(h->loss_acc); cudaFree(h->min_losses); cudaFree(h->flags);
@@ -453,6 +497,13 @@ extern "C" int metrpo_fit_create(const metrpo_fit_cfg* cfg, metrpo_fit_t** out) 
   if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) {
     fit_free(h);
     return set_error(METRPO_ERR_CUDA, "fit_create: cublasCreate failed");
+  }
+  e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+  for (cudaEvent_t* ev : {&h->ev_fork, &h->ev_w2, &h->ev_d1, &h->ev_join})
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    fit_free(h);
+    return set_error(METRPO_ERR_CUDA, "fit_create: %s", cudaGetErrorString(e));
   }
   *out = h;
   return METRPO_OK;
@@ -561,7 +612,7 @@ static int own_gemm(metrpo_fit* h, int M, int N, int Kd, const float* A, long lo
   GemmParams p;
   p.M = M; p.N = N; p.Kd = Kd; p.a_mn = a_mn; p.b_mn = b_mn; p.epi = epi; p.trans_store = trans_store;
   p.round_out = (epi != GEMM_EPI_PLAIN) ? 1 : 0;   // H1 / dH1 / dH0 feed later GEMMs
-  p.C = C; p.ldc = ldc; p.strideC = sC; p.bias = bias; p.strideBias = h->d.P; p.colsum = colsum;
+  p.C = C; p.ldc = ldc; p.strideC = sC; p.bias = bias; p.strideBias = h->d.P; p.colsum = colsum; p.dbg = nullptr;
   GemmOperands o;
   o.A = A; o.lda = lda; o.strideA = sA; o.a_ext = a_ext; o.a_kext = a_kext;
   o.B = B; o.ldb = ldb; o.strideB = sB; o.b_ext = b_ext; o.b_kext = b_kext;
@@ -580,12 +631,12 @@ static int fit_forward(metrpo_fit* h, const float* x, const float* y, int n_data
   const bool own = h->cfg.precision == METRPO_FIT_TF32;
   const int eb = static_cast<int>(std::min<long long>((static_cast<long long>(rows) * d.H / 4 + 255) / 256, 1184));
   int rc;
-  if (d.H % L0_COLS == 0) {
+  if (!own && d.H % L0_COLS == 0) {   // fp32 fidelity mode: layer 0 on the CUDA cores inside the gather pass
     const size_t smem0 = (static_cast<size_t>((L0_ROWS * (d.Din + 1) + 3) & ~3) + static_cast<size_t>(d.Din) * L0_COLS) * 4;
     fit_layer0_kernel<<<dim3((rows + L0_ROWS - 1) / L0_ROWS, d.H / L0_COLS, d.K), 256, smem0, st>>>(
         d, x, y, n_data, idx, identity, row0, seed, offset, rows, h->norm, h->theta, h->Z, h->XS, h->Y, h->H0, sZ, sS, sH);
     launches += 1;
-  } else {   // hidden widths that are not a multiple of 128: gather, then layer 0 as a GEMM
+  } else {   // gather, then layer 0 as a GEMM (one 32-deep K block: Din <= 88 is zero padded to Dp)
     dim3 blk(32, 8), grd((rows + 7) / 8, d.K);
     fit_gather_kernel<<<grd, blk, 0, st>>>(d, x, y, n_data, idx, identity, row0, seed, offset, rows, h->norm,
                                           h->Z, h->XS, h->Y, sZ, sS);
@@ -644,19 +695,30 @@ extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, 
   int nslab;
   if (own) {
     nslab = fit_gemm_colsum_slabs(batch, d.H);
+    // The weight-gradient GEMMs (side stream) run next to the data-gradient GEMMs (caller's stream):
+    //   side:  dW2 ............ | wait dH1 | dW1 .......................... |
+    //   main:  dH1 ... | wait dW2 (it reads H1, whose buffer dH0 reuses) | dH0 ... dW0 | join
+    cudaStream_t sd = h->side;
+    METRPO_CUDA_OK(cudaEventRecord(h->ev_fork, st));
+    METRPO_CUDA_OK(cudaStreamWaitEvent(sd, h->ev_fork, 0));
     // dW2[H,S] = H1^T dO: A = H1 [k = row][m] MN-major, B = dO [k = row][n = Sp] MN-major
     rc = own_gemm(h, d.H, d.S, batch, h->H1, d.H, sH, 1, d.H, h->O, d.Sp, sO, 1, d.Sp, h->grad + d.oW2, d.Sp, P,
-                  GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 0, st);
+                  GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 0, sd);
     if (rc != METRPO_OK) return rc;
+    METRPO_CUDA_OK(cudaEventRecord(h->ev_w2, sd));
     // dH1 = (dO W2^T) * (H1 > 0), db1 = column sums: A = dO [rows][Sp] K-major, B = W2 [n = H][k = Sp] K-major
     rc = own_gemm(h, batch, d.H, d.Sp, h->O, d.Sp, sO, 0, batch, h->theta + d.oW2, d.Sp, P, 0, d.H, h->D1, d.H, sH,
                   GEMM_EPI_MASK, nullptr, h->H1, h->part1, 0, st);
     if (rc != METRPO_OK) return rc;
+    METRPO_CUDA_OK(cudaEventRecord(h->ev_d1, st));
+    METRPO_CUDA_OK(cudaStreamWaitEvent(sd, h->ev_d1, 0));
     // dW1 = H0^T dH1: both operands MN-major, reduction over the rows
     rc = own_gemm(h, d.H, d.H, batch, h->H0, d.H, sH, 1, d.H, h->D1, d.H, sH, 1, d.H, h->grad + d.oW1, d.H, P,
-                  GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 0, st);
+                  GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 0, sd);
     if (rc != METRPO_OK) return rc;
-    // dH0 = (dH1 W1^T) * (H0 > 0) -> H1's buffer (H1 is dead now), db0 = column sums: both operands K-major
+    METRPO_CUDA_OK(cudaEventRecord(h->ev_join, sd));
+    // dH0 = (dH1 W1^T) * (H0 > 0) -> H1's buffer (H1 is dead once dW2 has read it), db0 = column sums
+    METRPO_CUDA_OK(cudaStreamWaitEvent(st, h->ev_w2, 0));
     rc = own_gemm(h, batch, d.H, d.H, h->D1, d.H, sH, 0, batch, h->theta + d.oW1, d.H, P, 0, d.H, h->H1, d.H, sH,
                   GEMM_EPI_MASK, nullptr, h->H0, h->part0, 0, st);
     if (rc != METRPO_OK) return rc;
@@ -665,6 +727,7 @@ extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, 
     rc = own_gemm(h, d.H, d.Din, batch, h->H1, d.H, sH, 1, d.H, h->Z, d.Dp, sZ, 1, d.Dp, h->grad + d.oW0, d.H, P,
                   GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 1, st);
     if (rc != METRPO_OK) return rc;
+    METRPO_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join, 0));
     launches += 5;
   } else {
     nslab = (batch + COLSUM_ROWS - 1) / COLSUM_ROWS;
@@ -680,7 +743,7 @@ extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, 
     METRPO_BLAS_OK(gemm_rm(h, true, false, d.Din, d.H, batch, h->Z, d.Dp, sZ, h->H1, d.H, sH, h->grad + d.oW0, d.H, P));
     launches += 7;
   }
-  fit_bias_grad_finish_kernel<<<dim3((2 * d.H + d.S + 255) / 256, d.K), 256, 0, st>>>(
+  fit_bias_grad_finish_kernel<<<dim3((2 * d.H + d.S + 31) / 32, d.K), 256, 0, st>>>(
       d, h->part1, h->part0, nslab, h->part2, mb, h->grad);
   // Adam (tf.train.AdamOptimizer defaults beta1 0.9, beta2 0.999, epsilon 1e-8)
   h->adam_t += 1;

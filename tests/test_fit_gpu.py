@@ -58,7 +58,7 @@ def test_train_steps_match_oracle(dims, precision, ltol, wtol):
         l_dev = fit.step(xd, yd, batch, 1e-3, idx=idx).cpu().numpy()
         l_ref = of.train_step(ref, adam, norm, x, y, idx, batch, 1e-3, S, drop)
         np.testing.assert_allclose(l_dev, l_ref, rtol=ltol, atol=ltol)
-    assert fit.last_launches() == ((12 if H % 128 == 0 else 13) if precision == "tf32" else (15 if H % 128 == 0 else 17))
+    assert fit.last_launches() == (13 if precision == "tf32" else (15 if H % 128 == 0 else 17))
     for k in range(K):
         w = fit.get_weights(k)
         for key in w:
