@@ -316,6 +316,34 @@ def run_cuda(args, rank, local_rank, world):
     except Exception as exc:   # reported, never fatal for the headline metric
         trpo_info = {"error": repr(exc)}
 
+    # ---- the ensemble-fit iteration of the same config: K models x batch 1000, all
+    #      contractions on the tcgen05 TF32 GEMM; reported next to the headline, never part of it ----
+    fit_info = None
+    if rank == 0:
+        try:
+            from me_trpo_b200.dynamics import EnsembleFit
+            S_, A_, drop_ = spec["S"], spec["A"], spec["drop"]
+            fb, fn = 1000, 200000
+            fit = EnsembleFit(S_, A_, drop_, HIDDEN, K_MODELS, max_rows=1024, precision="tf32")
+            fit.set_ensemble(models)                 # the synthetic ensemble the rollout above used
+            fit.set_normalization(**norm); fit.reset_adam()
+            xd = torch.randn(fn, S_ + A_, device=dev); yd = xd[:, :S_] + 0.1 * torch.randn(fn, S_, device=dev)
+            for j in range(5):
+                fit.step(xd, yd, fb, 1e-3, seed=1, offset=j, want_losses=False)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for j in range(50):
+                fit.step(xd, yd, fb, 1e-3, seed=1, offset=5 + j, want_losses=False)
+            f1.record(); torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1) / 50
+            fit_info = {"ms": fms, "samples_per_s": K_MODELS * fb / (fms * 1e-3), "launches": fit.last_launches(),
+                        "what": "one Adam step of all %d models on independent minibatches of %d rows (gather, "
+                                "forward, MSE, backward, Adam; TF32 tcgen05 GEMMs, fp32 accumulate)" % (K_MODELS, fb)}
+            fit.close()
+        except Exception as exc:
+            fit_info = {"error": repr(exc)}
+
     units_per_step = K_MODELS * B_ROWS * T * world
     value = units_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = units_per_step * args.steps / (total_ms_e2e * 1e-3)
@@ -369,6 +397,7 @@ def run_cuda(args, rank, local_rank, world):
             "gpu_launches": args.steps * ro.last_launches(),
             "rollout_kernel_variant": {0: "single-stream", 1: "two-stream", 2: "two-stream, column split"}[kernel_variant],
             "clocks": clocks, "finite": finite, "trpo_half_of_iteration": trpo_info,
+            "fit_iteration": fit_info,
         }
         print(json.dumps(line), flush=True)
     ro.close()

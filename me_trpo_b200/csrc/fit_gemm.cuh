@@ -358,7 +358,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                         CUtensorMapFloatOOBfill);
-inline PFN_tmapEncodeTiled fit_tmap_encoder() {
+static PFN_tmapEncodeTiled fit_tmap_encoder() {
   static PFN_tmapEncodeTiled fn = nullptr;
   if (!fn) {
     void* ptr = nullptr;
@@ -401,8 +401,10 @@ struct GemmOperands {
   const float* B; long long ldb, strideB; int b_ext, b_kext;   //   zero padded); *_kext: K extent (0: Kd)
   const float* aux; long long ldaux, strideAux;                // GEMM_EPI_MASK
 };
+// (internal linkage: the function-local `attr_set` flag must not be unified between libmetrpo.so and
+// libmetrpo_dev.so, each of which carries its own copy of the kernel)
 template <int MT, int BN>
-inline int fit_gemm_launch_t(const GemmParams& p, const GemmOperands& o, int models, cudaStream_t st) {
+static int fit_gemm_launch_t(const GemmParams& p, const GemmOperands& o, int models, cudaStream_t st) {
   using Cfg = GemmCfg<MT, BN>;
   CUtensorMap tmA, tmB, tmC, tmAux;
   int r = fit_make_tmap(&tmA, o.A, p.a_mn, o.a_ext, o.a_kext ? o.a_kext : p.Kd, o.lda, models, o.strideA, Cfg::BM);
