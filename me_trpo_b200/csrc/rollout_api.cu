@@ -160,6 +160,7 @@ struct metrpo_rollout {
   float* duo_rbuf = nullptr; unsigned* duo_rctr = nullptr;
   size_t duo_pbuf_stride = 0, duo_rbuf_stride = 0;
   uint32_t duo_tm_z = 0;
+  int duo_pol_rows = 32;
   uint32_t d_off_stage, d_off_sw0g, d_off_sw2, d_off_scr[2], d_off_hid[2], d_off_list[2], d_off_sbias,
       d_off_snorm, d_off_spol, d_off_bars, d_smem_bytes;
   int last_kernel = 0;        // 0: single-stream, 1: duo cs = 1, 2: duo cs = 2, 3: fp32 fidelity path
@@ -368,19 +369,25 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     const bool tmem_fits = h->tm_z + (h->K0 / 2) <= 512;          // one Z slot always; two when they fit
     const bool shape_ok = !fp32 && !h->big && c.n_models > 1 && h->n_tiles >= 2 && (h->KC % 2) == 0 &&
                           2 * c.n_models <= h->num_sms;
-    uint32_t q = 0;
-    h->d_off_stage = q; q += NSTAGE * h->stage_bytes;
-    h->d_off_sw0g = q; q += 2 * h->w0g_bytes;
-    q = align_up(q, 1024); h->d_off_sw2 = q; q += h->w2chunk_bytes;
-    const uint32_t scr_bytes = align_up(std::max(32, c.state_dim + c.action_dim + 1) * TILE_M * 4, 16);
-    for (int g = 0; g < 2; ++g) { h->d_off_scr[g] = q; q += scr_bytes; }
-    for (int g = 0; g < 2; ++g) { h->d_off_hid[g] = q; q += 2 * DUO_POL_ROWS * 33 * 4; }
-    for (int g = 0; g < 2; ++g) { h->d_off_list[g] = q; q += (TILE_M + 4) * 4; }
-    h->d_off_sbias = q; q += (c.hidden + BIAS_PAD) * 4;      // b1 of at most all passes | b2
-    h->d_off_snorm = q; q += align_up((2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4, 16);
-    h->d_off_spol = q; q += align_up(h->pol_floats * 4, 16);
-    h->d_off_bars = q; q += D_NUM_BARS * 8;
-    h->d_smem_bytes = q + 1024;
+    // the hidden-activation scratch of the policy pass is the one elastic item: 32 owned rows per pass
+    // when it fits, 16 or 8 when the K0 = 48 shapes (ant) would exceed the shared-memory limit
+    for (h->duo_pol_rows = DUO_POL_ROWS; h->duo_pol_rows >= 8; h->duo_pol_rows /= 2) {
+      uint32_t q = 0;
+      h->d_off_stage = q; q += NSTAGE * h->stage_bytes;
+      h->d_off_sw0g = q; q += 2 * h->w0g_bytes;
+      q = align_up(q, 1024); h->d_off_sw2 = q; q += h->w2chunk_bytes;
+      const uint32_t scr_bytes = align_up(std::max(32, c.state_dim + c.action_dim + 1) * TILE_M * 4, 16);
+      for (int g = 0; g < 2; ++g) { h->d_off_scr[g] = q; q += scr_bytes; }
+      for (int g = 0; g < 2; ++g) { h->d_off_hid[g] = q; q += 2 * h->duo_pol_rows * 33 * 4; }
+      for (int g = 0; g < 2; ++g) { h->d_off_list[g] = q; q += (TILE_M + 4) * 4; }
+      h->d_off_sbias = q; q += (c.hidden + BIAS_PAD) * 4;      // b1 of at most all passes | b2
+      h->d_off_snorm = q; q += align_up((2 * (c.state_dim + c.action_dim) + 2 * c.state_dim) * 4, 16);
+      h->d_off_spol = q; q += align_up(h->pol_floats * 4, 16);
+      h->d_off_bars = q; q += D_NUM_BARS * 8;
+      h->d_smem_bytes = q + 1024;
+      if (h->d_smem_bytes + 64 <= static_cast<uint32_t>(prop.sharedMemPerBlockOptin)) break;
+    }
+    if (h->duo_pol_rows < 8) h->duo_pol_rows = 8;
     h->duo_ok = shape_ok && tmem_fits && h->d_smem_bytes + 64 <= static_cast<uint32_t>(prop.sharedMemPerBlockOptin) &&
                 h->duo_mode != 0;
     if (h->duo_ok) {
@@ -725,6 +732,7 @@ static int launch(metrpo_rollout* h, KParams& p, cudaStream_t st) {
       std::memset(&dpar, 0, sizeof(dpar));
       dpar.cs = best_cs; dpar.NCp = NCtot / best_cs; dpar.n_pairs = h->n_pairs;
       dpar.z_shared = (h->tm_z + 2 * (h->K0 / 2) > 512) ? 1 : 0;
+      dpar.pol_rows = h->duo_pol_rows;
       const int slots = best_ctas / (K * best_cs);
       // schedule over tile PAIRS: key space disjoint from the single-stream schedules
       const long long key = (static_cast<long long>(0x40000000 | slots) << 32) | static_cast<unsigned>(p.n_steps);

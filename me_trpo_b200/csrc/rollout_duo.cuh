@@ -47,7 +47,8 @@ __device__ __forceinline__ void setmaxnreg_dec_lo() {
 __device__ __forceinline__ void setmaxnreg_inc_hi() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DUO_REGS_HI));
 }
-constexpr int DUO_POL_ROWS = 32;                    // owned rows per policy pass (2 threads per row)
+constexpr int DUO_POL_ROWS = 32;                    // owned rows per policy pass (2 threads per row); DuoParams::pol_rows
+                                                    // shrinks it to 16 / 8 when shared memory is tight (K0 = 48 shapes)
 
 enum {
   D_FULL = 0,        // [NSTAGE] W1 stage landed (tx)
@@ -80,6 +81,7 @@ struct DuoParams {
   unsigned* rctr;               // [slot*2 + stream]
   unsigned long long rbuf_stride;
   uint32_t off_scr[2], off_hid[2], off_list[2];   // per-stream shared memory areas
+  int pol_rows;                 // owned rows per policy pass: DUO_POL_ROWS, or 16 / 8 (sizes the hidden-activation scratch)
   int z_shared;                 // 1: TMEM has room for ONE Z operand only (K0 = 48, ant): the streams take
                                 //    turns, a group writes its Z after the other stream's last L0 retired
 };
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
       const float* dMean = sNorm + 2 * p.SA;
       const float* dStd = sNorm + 2 * p.SA + S;
       float* scrA = reinterpret_cast<float*>(smem + dp.off_scr[grp]);
-      float* sHid = reinterpret_cast<float*>(smem + dp.off_hid[grp]);     // [2][DUO_POL_ROWS][33]
+      float* sHid = reinterpret_cast<float*>(smem + dp.off_hid[grp]);     // [2][pol_rows][33]
       int* sList = reinterpret_cast<int*>(smem + dp.off_list[grp]);        // [128] + sCnt[4]
       int* sCnt = sList + TILE_M;
       const uint32_t ztm = tmem + lane_base + p.tm_z + grp * zcols;
@@ -757,8 +759,9 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
             if (want_pol) {
               const int part = e & 1, jl = e >> 1;
               const int nl = p.n_pol_layers;
-              for (int base = 0; base < n_mine; base += DUO_POL_ROWS) {
-                if (jl < DUO_POL_ROWS) {
+              const int PR = dp.pol_rows;
+              for (int base = 0; base < n_mine; base += PR) {
+                if (jl < PR) {
                   const int j = base + jl;
                   const bool actv = j < n_mine;
                   const float* cur = scrA + (actv ? j : 0) * SPs;
@@ -787,11 +790,11 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
                         acc[4 * q] = r0.x; acc[4 * q + 1] = r0.y; acc[4 * q + 2] = r1.x; acc[4 * q + 3] = r1.y;
                       }
                     }
-                    float* out = sHid + (l & 1) * (DUO_POL_ROWS * 33) + jl * 33 + 16 * part;
+                    float* out = sHid + (l & 1) * (PR * 33) + jl * 33 + 16 * part;
 #pragma unroll
                     for (int q = 0; q < 16; ++q) out[q] = fast_tanh(acc[q]);
                     __syncwarp();
-                    cur = sHid + (l & 1) * (DUO_POL_ROWS * 33) + jl * 33;
+                    cur = sHid + (l & 1) * (PR * 33) + jl * 33;
                   }
                   const PolicyLayer& L = p.pl[nl - 1];
                   float mo[AMAX / 2];

@@ -254,6 +254,10 @@ DUO = [
     ("duo_swimmer", "swimmer", 5, 700, 6, 5, 512, "step_rand", "philox"),
     # more pairs than gang slots: chains cut across slots, tile state handed over through row_state
     ("duo_hc_many_tiles", "half-cheetah", 5, 4096, 9, 100, 512, "step_rand", "philox"),
+    # ant: K0 = 48 -> ONE Z slot in TMEM taken in turns by the streams (z_shared), 8-row policy passes
+    # (shared memory), early-terminating paths (is_done) with resets from the pool
+    ("duo_ant", "ant", 4, 600, 7, 100, 512, "step_rand", "philox"),
+    ("duo_ant_k20", "ant", 20, 1024, 4, 3, 1024, "step_rand", "explicit"),
 ]
 
 
