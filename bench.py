@@ -319,7 +319,7 @@ def run_cuda(args, rank, local_rank, world):
     # ---- the ensemble-fit iteration of the same config: K models x batch 1000, all
     #      contractions on the tcgen05 TF32 GEMM; reported next to the headline, never part of it ----
     fit_info = None
-    if rank == 0:
+    if world == 1:      # single-GPU runs only: no rank may run ahead of a collective tear-down
         try:
             from me_trpo_b200.dynamics import EnsembleFit
             S_, A_, drop_ = spec["S"], spec["A"], spec["drop"]

@@ -32,6 +32,10 @@ namespace metrpo {
 
 constexpr uint32_t PHILOX_STREAM_FIT = 0x30000u;   // minibatch row indices
 
+// per-step scalars of a replayed CUDA graph of the training iteration (device copy, refreshed before
+// every launch): kernels that take a `dargs` pointer read these instead of their by-value arguments
+struct FitStepArgs { unsigned long long seed, offset; float lr_t; int pad; };
+
 struct FitDims {
   int S, A, SA, drop, Din, H, K;
   int rnd;                               // 1 (TF32 mode): producers round GEMM operands to TF32-nearest
@@ -48,9 +52,10 @@ __global__ void fit_gather_kernel(FitDims d, const float* __restrict__ x_data, c
                                   unsigned long long seed, unsigned long long offset, int rows,
                                   const float* __restrict__ norm, float* __restrict__ Z,
                                   float* __restrict__ XS, float* __restrict__ Y, long long strideZ,
-                                  long long strideS) {
+                                  long long strideS, const FitStepArgs* __restrict__ dargs) {
   const int r = blockIdx.x * blockDim.y + threadIdx.y, k = blockIdx.y;
   if (r >= rows) return;
+  if (dargs) { seed = dargs->seed; offset = dargs->offset; }
   int i;
   if (identity) i = row0 + r;
   else if (idx) i = idx[static_cast<size_t>(r) * d.K + k];
@@ -342,7 +347,8 @@ __global__ void __launch_bounds__(256) fit_bias_grad_finish_kernel(FitDims d, co
 // theta -= lr_t * m / (sqrt(v) + eps),  lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)  (host-computed)
 __global__ void fit_adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
                                 float* __restrict__ v, long long n4, float lr_t, float beta1, float beta2,
-                                float eps) {
+                                float eps, const FitStepArgs* __restrict__ dargs) {
+  if (dargs) lr_t = dargs->lr_t;
   float4* t4 = reinterpret_cast<float4*>(theta);
   const float4* g4 = reinterpret_cast<const float4*>(grad);
   float4* m4 = reinterpret_cast<float4*>(m);
@@ -414,11 +420,22 @@ struct metrpo_fit {
   // backward pass: weight-gradient GEMMs run on a side stream next to the data-gradient GEMMs
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_w2 = nullptr, ev_d1 = nullptr, ev_join = nullptr;
+  // CUDA graph of the training iteration (TF32 mode, Philox minibatches): captured on `cap` after one
+  // eager iteration with the same (x, y, n_data, batch, losses), replayed into the caller's stream
+  FitStepArgs* dargs = nullptr;
+  cudaStream_t cap = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  const float *gx = nullptr, *gy = nullptr; float* glosses = nullptr;
+  int gn = 0, gbatch = 0, gwarm = 0, glaunches = 0;
+  int use_graph = 1;
 };
 
 static void fit_free(metrpo_fit* h) {
   if (!h) return;
   if (h->blas) cublasDestroy(h->blas);
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  if (h->cap) cudaStreamDestroy(h->cap);
+  cudaFree(h->dargs);
   if (h->side) cudaStreamDestroy(h->side);
   for (cudaEvent_t e : {h->ev_fork, h->ev_w2, h->ev_d1, h->ev_join}) if (e) cudaEventDestroy(e);
   cudaFree(h->theta); cudaFree(h->grad); cudaFree(h->m); cudaFree(h->v); cudaFree(h->best);
@@ -499,6 +516,9 @@ extern "C" int metrpo_fit_create(const metrpo_fit_cfg* cfg, metrpo_fit_t** out) 
     return set_error(METRPO_ERR_CUDA, "fit_create: cublasCreate failed");
   }
   e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&h->dargs, sizeof(FitStepArgs));
+  { const char* ev = getenv("METRPO_FIT_GRAPH"); h->use_graph = ev ? atoi(ev) : 1; }
   for (cudaEvent_t* ev : {&h->ev_fork, &h->ev_w2, &h->ev_d1, &h->ev_join})
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
   if (e != cudaSuccess) {
@@ -625,7 +645,7 @@ static int own_gemm(metrpo_fit* h, int M, int N, int Kd, const float* A, long lo
 // gather + forward of `rows` rows per model; leaves O = H1 W2 (bias b2 is added by fit_mse_kernel)
 static int fit_forward(metrpo_fit* h, const float* x, const float* y, int n_data, const int* idx, int identity,
                        int row0, unsigned long long seed, unsigned long long offset, int rows, cudaStream_t st,
-                       int& launches) {
+                       int& launches, const FitStepArgs* dargs = nullptr) {
   const FitDims& d = h->d;
   const long long R = h->R, sZ = R * d.Dp, sS = R * d.S, sO = R * d.Sp, sH = R * d.H, P = d.P;
   const bool own = h->cfg.precision == METRPO_FIT_TF32;
@@ -639,7 +659,7 @@ static int fit_forward(metrpo_fit* h, const float* x, const float* y, int n_data
   } else {   // gather, then layer 0 as a GEMM (one 32-deep K block: Din <= 88 is zero padded to Dp)
     dim3 blk(32, 8), grd((rows + 7) / 8, d.K);
     fit_gather_kernel<<<grd, blk, 0, st>>>(d, x, y, n_data, idx, identity, row0, seed, offset, rows, h->norm,
-                                          h->Z, h->XS, h->Y, sZ, sS);
+                                          h->Z, h->XS, h->Y, sZ, sS, dargs);
     if (own) {   // H0 = relu(Z W0 + b0): A = Z [rows][Dp] (zero padded), B = W0 [k = Din][n = H] MN-major
       rc = own_gemm(h, rows, d.H, d.Dp, h->Z, d.Dp, sZ, 0, rows, h->theta + d.oW0, d.H, P, 1, d.H, h->H0, d.H, sH,
                     GEMM_EPI_BIAS_RELU, h->theta + d.ob0, nullptr, nullptr, 0, st, 0, d.Din);
@@ -671,23 +691,18 @@ static int fit_forward(metrpo_fit* h, const float* x, const float* y, int n_data
   return METRPO_OK;
 }
 
-extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, int n_data, const int32_t* idx,
-                               int batch, uint64_t seed, uint64_t offset, double lr, float* losses,
-                               void* stream) {
-  if (!h) return set_error(METRPO_ERR_INVALID, "fit_step: null handle");
-  if (!x || !y || n_data < 1) return set_error(METRPO_ERR_INVALID, "fit_step: x, y and n_data >= 1 are required");
-  if (batch < 1 || batch > h->R) return set_error(METRPO_ERR_INVALID, "fit_step: batch must be in [1, max_rows=%d]", h->R);
-  int rc = fit_check_ready(h, "fit_step");
-  if (rc != METRPO_OK) return rc;
-  METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// every launch of one training iteration on `st` (dargs != NULL: the per-step scalars come from device memory)
+static int fit_step_issue(metrpo_fit* h, const float* x, const float* y, int n_data, const int32_t* idx, int batch,
+                          uint64_t seed, uint64_t offset, float lr_t, float* losses, cudaStream_t st,
+                          const FitStepArgs* dargs) {
+  int rc;
   const bool own = h->cfg.precision == METRPO_FIT_TF32;
   if (!own) METRPO_BLAS_OK(cublasSetStream(h->blas, st));
   const FitDims& d = h->d;
   const long long R = h->R, sZ = R * d.Dp, sS = R * d.S, sO = R * d.Sp, sH = R * d.H, P = d.P;
   int launches = 0;
   METRPO_CUDA_OK(cudaMemsetAsync(h->loss_acc, 0, d.K * 8, st));
-  rc = fit_forward(h, x, y, n_data, idx, 0, 0, seed, offset, batch, st, launches);
+  rc = fit_forward(h, x, y, n_data, idx, 0, 0, seed, offset, batch, st, launches, dargs);
   if (rc != METRPO_OK) return rc;
   const int mb = std::min((batch + 7) / 8, 148);
   fit_mse_kernel<<<dim3(mb, d.K), 256, 8 * d.S * 4, st>>>(d, h->O, h->XS, h->Y, h->theta, h->norm, batch, 1.0 / batch, 1,
@@ -746,17 +761,70 @@ extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, 
   fit_bias_grad_finish_kernel<<<dim3((2 * d.H + d.S + 31) / 32, d.K), 256, 0, st>>>(
       d, h->part1, h->part0, nslab, h->part2, mb, h->grad);
   // Adam (tf.train.AdamOptimizer defaults beta1 0.9, beta2 0.999, epsilon 1e-8)
-  h->adam_t += 1;
-  const double b1 = 0.9, b2 = 0.999;
-  const double lr_t = lr * std::sqrt(1.0 - std::pow(b2, (double)h->adam_t)) / (1.0 - std::pow(b1, (double)h->adam_t));
   const long long n4 = P * d.K / 4;
   fit_adam_kernel<<<static_cast<int>(std::min<long long>((n4 + 255) / 256, 148 * 8)), 256, 0, st>>>(
-      h->theta, h->grad, h->m, h->v, n4, static_cast<float>(lr_t), 0.9f, 0.999f, 1e-8f);
+      h->theta, h->grad, h->m, h->v, n4, lr_t, 0.9f, 0.999f, 1e-8f, dargs);
   launches += 3;
   if (losses) { fit_losses_out_kernel<<<1, 64, 0, st>>>(h->loss_acc, losses, d.K); ++launches; }
   METRPO_CUDA_OK(cudaGetLastError());
   h->last_launches = launches;
   return METRPO_OK;
+}
+
+extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, int n_data, const int32_t* idx,
+                               int batch, uint64_t seed, uint64_t offset, double lr, float* losses,
+                               void* stream) {
+  if (!h) return set_error(METRPO_ERR_INVALID, "fit_step: null handle");
+  if (!x || !y || n_data < 1) return set_error(METRPO_ERR_INVALID, "fit_step: x, y and n_data >= 1 are required");
+  if (batch < 1 || batch > h->R) return set_error(METRPO_ERR_INVALID, "fit_step: batch must be in [1, max_rows=%d]", h->R);
+  int rc = fit_check_ready(h, "fit_step");
+  if (rc != METRPO_OK) return rc;
+  METRPO_CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+  h->adam_t += 1;
+  const double b1 = 0.9, b2 = 0.999;
+  const float lr_t = static_cast<float>(lr * std::sqrt(1.0 - std::pow(b2, (double)h->adam_t)) / (1.0 - std::pow(b1, (double)h->adam_t)));
+
+  // Replay path: the 13 launches + 4 event edges of an iteration as ONE graph launch.  The first call
+  // with a given (x, y, n_data, batch, losses) runs eagerly, the second captures, later ones replay; the
+  // scalars that change per step (Philox seed / offset, lr_t) travel through h->dargs.
+  const bool graphable = h->use_graph && h->cfg.precision == METRPO_FIT_TF32 && idx == nullptr;
+  if (graphable) {
+    if (h->gx != x || h->gy != y || h->gn != n_data || h->gbatch != batch || h->glosses != losses) {
+      if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+      h->gx = x; h->gy = y; h->gn = n_data; h->gbatch = batch; h->glosses = losses; h->gwarm = 0;
+    }
+    FitStepArgs ha;
+    ha.seed = seed; ha.offset = offset; ha.lr_t = lr_t; ha.pad = 0;
+    METRPO_CUDA_OK(cudaMemcpyAsync(h->dargs, &ha, sizeof(ha), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    if (h->gwarm >= 1 && !h->gexec) {
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        rc = fit_step_issue(h, x, y, n_data, nullptr, batch, seed, offset, lr_t, losses, h->cap, h->dargs);
+        const cudaError_t ce = cudaStreamEndCapture(h->cap, &graph);
+        if (rc == METRPO_OK && ce == cudaSuccess && graph &&
+            cudaGraphInstantiate(&h->gexec, graph, 0) == cudaSuccess) {
+          h->glaunches = h->last_launches;
+        } else {
+          h->gexec = nullptr; h->use_graph = 0;     // capture not possible here: stay on the eager path
+          cudaGetLastError();
+        }
+        if (graph) cudaGraphDestroy(graph);
+      } else {
+        h->use_graph = 0;
+        cudaGetLastError();
+      }
+    }
+    if (h->gexec) {
+      METRPO_CUDA_OK(cudaGraphLaunch(h->gexec, st));
+      h->last_launches = h->glaunches;
+      return METRPO_OK;
+    }
+    h->gwarm += 1;
+    return fit_step_issue(h, x, y, n_data, nullptr, batch, seed, offset, lr_t, losses, st, h->dargs);
+  }
+  return fit_step_issue(h, x, y, n_data, idx, batch, seed, offset, lr_t, losses, st, nullptr);
 }
 
 extern "C" int metrpo_fit_eval(metrpo_fit_t* h, const float* x, const float* y, int n, int snapshot, float* losses,

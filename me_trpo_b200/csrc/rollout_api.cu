@@ -366,7 +366,11 @@ extern "C" int metrpo_rollout_create(const metrpo_rollout_cfg* cfg, metrpo_rollo
     h->duo_mode = ev ? atoi(ev) : -1;
     h->n_pairs = (h->n_tiles + 1) / 2;
     h->duo_tm_z = h->tm_z;
-    const bool tmem_fits = h->tm_z + (h->K0 / 2) <= 512;          // one Z slot always; two when they fit
+    // one Z slot always; two when they fit (else the streams take turns on it: z_shared).  METRPO_DUO_ZSHARED=0
+    // keeps the K0 = 48 shapes (ant) on the single-stream kernel.
+    const char* evz = getenv("METRPO_DUO_ZSHARED");
+    const bool allow_zs = evz ? atoi(evz) != 0 : true;
+    const bool tmem_fits = h->tm_z + (allow_zs ? 1 : 2) * (h->K0 / 2) <= 512;
     const bool shape_ok = !fp32 && !h->big && c.n_models > 1 && h->n_tiles >= 2 && (h->KC % 2) == 0 &&
                           2 * c.n_models <= h->num_sms;
     // the hidden-activation scratch of the policy pass is the one elastic item: 32 owned rows per pass

@@ -760,6 +760,9 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
               const int part = e & 1, jl = e >> 1;
               const int nl = p.n_pol_layers;
               const int PR = dp.pol_rows;
+              // lanes of this warp that take part (a partial warp when pol_rows = 8): the two threads of a
+              // row exchange their halves of a hidden layer through sHid under this mask
+              const unsigned pmask = __ballot_sync(0xffffffffu, jl < PR);
               for (int base = 0; base < n_mine; base += PR) {
                 if (jl < PR) {
                   const int j = base + jl;
@@ -793,7 +796,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
                     float* out = sHid + (l & 1) * (PR * 33) + jl * 33 + 16 * part;
 #pragma unroll
                     for (int q = 0; q < 16; ++q) out[q] = fast_tanh(acc[q]);
-                    __syncwarp();
+                    __syncwarp(pmask);
                     cur = sHid + (l & 1) * (PR * 33) + jl * 33;
                   }
                   const PolicyLayer& L = p.pl[nl - 1];
@@ -834,7 +837,7 @@ __global__ void __launch_bounds__(DUO_THREADS, 1) rollout_duo_kernel(const __gri
                       }
                     }
                   }
-                  __syncwarp();
+                  __syncwarp(pmask);
                 }
               }
             }
