@@ -310,7 +310,7 @@ def run_cuda(args, rank, local_rank, world):
         iv = info.cpu().numpy()
         trpo_info = {"ms": float(tms.item()), "samples_per_gpu": N, "accepted": bool(iv[4] == 1.0),
                      "mean_kl": float(iv[2]), "allreduce": pu.allreduce_mode,
-                     "what": "process_samples + baseline fit + TRPO update (1 gradient, 11 "
+                     "what": "process_samples + baseline fit + TRPO update (1 gradient, 10 "
                      "Fisher-vector products, line search) on the last step's trajectory, device resident"}
         pu.close()
     except Exception as exc:   # reported, never fatal for the headline metric

@@ -17,6 +17,7 @@
 // gradients are tile-level outer products accumulated per block and flushed once with fp64 atomics.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -464,16 +465,28 @@ __global__ void __launch_bounds__(CTRL_THREADS) k_cg_step(int P, int logstd_off,
 }
 
 // initial_step_size = sqrt(2 max_kl / (d.Hd + 1e-8)); descent = step0 * d   (A.2)
+//
+// from_residual != 0: d.Hd is taken from the conjugate-gradient recurrence instead of one more
+// Fisher-vector pass over all samples: CG maintains r = g - H x, so d.(H d) = d.(g - r) with the same
+// regularised operator (rllab evaluates Hx(d) explicitly; the two agree to the rounding of the fp64
+// recurrence, ~1e-7 relative, far below the fp32 noise of a Fisher-vector pass).
 __global__ void __launch_bounds__(CTRL_THREADS) k_step_finish(int P, int logstd_off, int A, double* acc,
-                                                              double* cg, double reg, double max_kl) {
+                                                              double* cg, double reg, double max_kl,
+                                                              int from_residual) {
   __shared__ double sred[CTRL_THREADS / 32];
   double* x = cg + P; double* prev = cg + 4 * P; double* desc = cg + 5 * P; double* sc = cg + 6 * P;
+  const double* g = cg; const double* r = cg + 2 * P;
   const double N = sc[CGS_N];
   double dhd = 0.0;
   for (int e = threadIdx.x; e < P; e += CTRL_THREADS) {
-    double ze = acc[e] / N;
-    if (e >= logstd_off && e < logstd_off + A) ze = logstd_hess(prev[e]) * x[e];
-    ze += reg * x[e];
+    double ze;
+    if (from_residual) {
+      ze = g[e] - r[e];
+    } else {
+      ze = acc[e] / N;
+      if (e >= logstd_off && e < logstd_off + A) ze = logstd_hess(prev[e]) * x[e];
+      ze += reg * x[e];
+    }
     dhd += x[e] * ze;
   }
   dhd = block_sum(dhd, sred);
@@ -1278,11 +1291,16 @@ extern "C" int metrpo_trpo_update(metrpo_trpo_t* h, long long N, const float* ob
     k_cg_step<<<1, CTRL_THREADS, 0, st>>>(P, pd.logstd_off, A, h->acc, h->cg, h->vec_f, h->flags, reg_coeff,
                                           it == cg_iters - 1 ? 1 : 0); ++h->last_launches;
   }
-  // step0 from d.Hx(d)
+  // step0 from d.Hx(d): by default from the CG residual (r = g - Hx is maintained by the recurrence),
+  // METRPO_TRPO_EXPLICIT_SHS=1 runs rllab's explicit extra Fisher-vector pass instead
+  static const bool explicit_shs = [] { const char* ev = getenv("METRPO_TRPO_EXPLICIT_SHS"); return ev && atoi(ev) != 0; }();
   p.skip_flag = nullptr;
-  if ((rc = launch_pass<MODE_FVP>(h, p, st)) != METRPO_OK) return rc;
-  if ((rc = allreduce(h, h->acc, P + ACC_EXTRA, st)) != METRPO_OK) return rc;
-  k_step_finish<<<1, CTRL_THREADS, 0, st>>>(P, pd.logstd_off, A, h->acc, h->cg, reg_coeff, step_size); ++h->last_launches;
+  if (explicit_shs) {
+    if ((rc = launch_pass<MODE_FVP>(h, p, st)) != METRPO_OK) return rc;
+    if ((rc = allreduce(h, h->acc, P + ACC_EXTRA, st)) != METRPO_OK) return rc;
+  }
+  k_step_finish<<<1, CTRL_THREADS, 0, st>>>(P, pd.logstd_off, A, h->acc, h->cg, reg_coeff, step_size,
+                                            explicit_shs ? 0 : 1); ++h->last_launches;
 
   // back-tracking line search: ratio in backtrack_ratio ** arange(max_backtracks)
   p.vec = nullptr;

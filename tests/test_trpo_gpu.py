@@ -160,8 +160,9 @@ def test_update_matches_oracle_optimize(env, N):
     cos = step_dev.dot(step_ref) / (np.linalg.norm(step_dev) * np.linalg.norm(step_ref))
     assert cos >= 0.9999
     assert _rel(step_dev, step_ref) <= 5e-3
-    # grad + finish, 10 x (FVP + cg step), FVP + step, 15 x (prepare + loss + check), finalize
-    assert pu.last_launches() == 2 + 10 * 2 + 2 + 15 * 3 + 1
+    # grad + finish, 10 x (FVP + cg step), step (d.Hd from the CG residual: no 11th Fisher-vector pass),
+    # 15 x (prepare + loss + check), finalize
+    assert pu.last_launches() == 2 + 10 * 2 + 1 + 15 * 3 + 1
     pu.close()
 
 
