@@ -425,7 +425,7 @@ struct metrpo_fit {
   FitStepArgs* dargs = nullptr;
   cudaStream_t cap = nullptr;
   cudaGraphExec_t gexec = nullptr;
-  const float *gx = nullptr, *gy = nullptr; float* glosses = nullptr;
+  const float *gx = nullptr, *gy = nullptr;
   int gn = 0, gbatch = 0, gwarm = 0, glaunches = 0;
   int use_graph = 1;
 };
@@ -787,13 +787,13 @@ extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, 
   const float lr_t = static_cast<float>(lr * std::sqrt(1.0 - std::pow(b2, (double)h->adam_t)) / (1.0 - std::pow(b1, (double)h->adam_t)));
 
   // Replay path: the 13 launches + 4 event edges of an iteration as ONE graph launch.  The first call
-  // with a given (x, y, n_data, batch, losses) runs eagerly, the second captures, later ones replay; the
+  // with a given (x, y, n_data, batch) runs eagerly, the second captures, later ones replay; the
   // scalars that change per step (Philox seed / offset, lr_t) travel through h->dargs.
   const bool graphable = h->use_graph && h->cfg.precision == METRPO_FIT_TF32 && idx == nullptr;
   if (graphable) {
-    if (h->gx != x || h->gy != y || h->gn != n_data || h->gbatch != batch || h->glosses != losses) {
+    if (h->gx != x || h->gy != y || h->gn != n_data || h->gbatch != batch) {
       if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
-      h->gx = x; h->gy = y; h->gn = n_data; h->gbatch = batch; h->glosses = losses; h->gwarm = 0;
+      h->gx = x; h->gy = y; h->gn = n_data; h->gbatch = batch; h->gwarm = 0;
     }
     FitStepArgs ha;
     ha.seed = seed; ha.offset = offset; ha.lr_t = lr_t; ha.pad = 0;
@@ -801,7 +801,7 @@ extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, 
     if (h->gwarm >= 1 && !h->gexec) {
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        rc = fit_step_issue(h, x, y, n_data, nullptr, batch, seed, offset, lr_t, losses, h->cap, h->dargs);
+        rc = fit_step_issue(h, x, y, n_data, nullptr, batch, seed, offset, lr_t, nullptr, h->cap, h->dargs);
         const cudaError_t ce = cudaStreamEndCapture(h->cap, &graph);
         if (rc == METRPO_OK && ce == cudaSuccess && graph &&
             cudaGraphInstantiate(&h->gexec, graph, 0) == cudaSuccess) {
@@ -819,6 +819,11 @@ extern "C" int metrpo_fit_step(metrpo_fit_t* h, const float* x, const float* y, 
     if (h->gexec) {
       METRPO_CUDA_OK(cudaGraphLaunch(h->gexec, st));
       h->last_launches = h->glaunches;
+      if (losses) {   // the caller's loss buffer changes from call to call: outside the graph
+        fit_losses_out_kernel<<<1, 64, 0, st>>>(h->loss_acc, losses, h->d.K);
+        METRPO_CUDA_OK(cudaGetLastError());
+        ++h->last_launches;
+      }
       return METRPO_OK;
     }
     h->gwarm += 1;

@@ -166,3 +166,34 @@ def test_running_mean_std_and_data_split():
     assert dv.get_num_data() == 20 and dt.get_num_data() == 50          # 30 -> cap 20, 60 -> cap 50
     np.testing.assert_array_equal(dt.x.cpu().numpy(), x[40:])           # FIFO: oldest rows dropped
     np.testing.assert_allclose(orms.mean.cpu().numpy(), (y[30:] - x[30:, :3]).sum(0) / (60 + 1e-2), rtol=1e-4, atol=1e-5)
+
+
+def test_graph_replay_equals_eager_iterations():
+    """TF32 mode, Philox minibatches: the CUDA-graph replay of the iteration (second call onwards) leaves
+    bit-identical weights to the eager launch sequence, with and without a per-call loss buffer."""
+    import os
+    S, A, drop, H, K = 18, 6, 1, 256, 3
+    models, norm, x, y = _problem(5, S, A, drop, H, K, n=2000)
+    xd, yd = torch.as_tensor(x).cuda(), torch.as_tensor(y).cuda()
+    res = {}
+    for flag in ("0", "1"):
+        old = os.environ.get("METRPO_FIT_GRAPH")
+        os.environ["METRPO_FIT_GRAPH"] = flag
+        try:
+            fit = _fit(models, norm, S, A, drop, H, "tf32")
+        finally:
+            if old is None:
+                os.environ.pop("METRPO_FIT_GRAPH", None)
+            else:
+                os.environ["METRPO_FIT_GRAPH"] = old
+        losses = []
+        for j in range(6):
+            l = fit.step(xd, yd, 200, 1e-3, seed=3, offset=j, want_losses=(j % 2 == 0))
+            if l is not None:
+                losses.append(l.cpu().numpy())
+        res[flag] = ([{k: v.cpu().numpy() for k, v in fit.get_weights(m).items()} for m in range(K)], losses)
+        fit.close()
+    for m in range(K):
+        for key in res["0"][0][m]:
+            np.testing.assert_array_equal(res["0"][0][m][key], res["1"][0][m][key])
+    np.testing.assert_allclose(np.array(res["0"][1]), np.array(res["1"][1]), rtol=1e-6)
