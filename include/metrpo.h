@@ -313,8 +313,9 @@ int metrpo_trpo_grad(metrpo_trpo_t* h, long long N, const float* obs, const floa
  * per-model best snapshots live on the device in fp32.  x rows are [state, action] (S + A),
  * y rows are next states (S) -- the data_collection layout (utils.py:44-131).
  * ============================================================================================= */
-enum { METRPO_FIT_TF32 = 0,   /* GEMMs on TF32 tensor cores, fp32 accumulate (default) */
-       METRPO_FIT_FP32 = 1 }; /* GEMMs in true fp32 (the reference's tf.matmul arithmetic) */
+enum { METRPO_FIT_TF32 = 0,   /* every contraction on the tcgen05 tensor cores through the library's own batched
+                                 TF32 GEMM (csrc/fit_gemm.cuh), fp32 accumulate (default) */
+       METRPO_FIT_FP32 = 1 }; /* fidelity mode: true fp32 products (the reference's tf.matmul arithmetic; cuBLAS) */
 
 typedef struct {
   int32_t state_dim;   /* S (<= 64) */
