@@ -21,6 +21,10 @@
 // (clipped at M, N by the tensor map); the masked variant also emits per-32-row-slab column sums (the
 // bias gradients), summed in a fixed order by the caller.
 //
+// Store clipping: the TMA unit clips rows at M exactly and columns at 16-byte granularity, i.e. up to the next
+// multiple of 4 columns past N may be written (with the epilogue of a zero accumulator: 0, or relu(0) = 0);
+// the fit's padded arrays (row pitch a multiple of 32 floats, pads kept at zero) rely on exactly that.
+//
 // Roofline: fp32 operands make this L2-bandwidth bound at 128-row tiles (48 KB per 32-deep K block
 // for 512 tensor-pipe cycles); the 256 x 256 tile halves the bytes per FLOP and leaves 80 CTAs for
 // the fit's shapes (K = 5 models x 4 x 4 tiles), one wave.

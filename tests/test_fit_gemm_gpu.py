@@ -70,3 +70,15 @@ def test_gemm_fused_epilogues(shape, epi):
 
 def test_gemm_five_models_wgrad_shape():
     _run(1024, 1024, 1000, 5, 1, 1, 0)     # dW1 = H0^T dH1: both operands MN-major, ragged reduction
+
+
+def test_gemm_random_shapes_fuzz():
+    """40 random (M, N, K, models, major-ness, epilogue) cases -- odd M, N not a multiple of 4 or 32,
+    K tails, single-row problems -- through tools/gemm_fuzz.py (also checks that nothing is written
+    beyond the clipped output)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "gemm_fuzz.py"), "7", "40"], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "failures: 0" in out.stdout, "\n".join(l for l in out.stdout.splitlines() if not l.startswith("ok"))
