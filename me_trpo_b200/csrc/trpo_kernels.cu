@@ -58,6 +58,9 @@ struct PassParams {
   long long N;
   double* acc;
   const int* skip_flag;
+  float* act_cache;        // tiled pass only, optional: hidden activations per 128-sample tile, [tile][hidden row][128].
+                           // The GRAD pass writes it, the Fisher-vector passes of the same update (same theta) read it
+                           // instead of recomputing the forward pass
 };
 
 // tanh(x) = 1 - 2/(exp(2x)+1) with ex2.approx / rcp.approx: abs error ~1e-7, ~6 instructions (the
@@ -867,6 +870,8 @@ struct metrpo_trpo {
   unsigned p2p_seq = 0;
   int last_launches = 0;
   int pass_impl = METRPO_TRPO_PASS_AUTO;
+  float* act_cache = nullptr;          // see PassParams::act_cache
+  size_t act_cache_floats = 0;
 };
 
 static void trpo_free(metrpo_trpo* h) {
@@ -1182,6 +1187,7 @@ static int fill_pass(metrpo_trpo* h, PassParams& p, long long N, const float* ob
   p.pd = h->pd; p.obs = obs; p.act = act; p.adv = adv; p.old_mean = old_mean; p.old_log_std = old_log_std;
   p.old_ls_stride = old_log_std_per_sample ? h->cfg.action_dim : 0;
   p.valid = valid; p.N = N; p.acc = h->acc; p.skip_flag = nullptr; p.vec = nullptr; p.theta = nullptr;
+  p.act_cache = nullptr;
   return METRPO_OK;
 }
 
@@ -1276,6 +1282,21 @@ extern "C" int metrpo_trpo_update(metrpo_trpo_t* h, long long N, const float* ob
   fill_pass(h, p, N, obs, act, adv, old_mean, old_log_std, old_log_std_per_sample, valid);
   METRPO_CUDA_OK(cudaMemsetAsync(h->acc, 0, (P + ACC_EXTRA) * 8, st));
 
+  // Hidden activations of the policy at theta are the same for the gradient pass and all Fisher-vector
+  // passes of this update: the gradient pass stores them (64 floats per sample for 32-32 policies, 1 GB at
+  // 4.1 M samples), the Fisher-vector passes load them instead of recomputing the forward pass.
+  static const bool use_act_cache = [] { const char* ev = getenv("METRPO_TRPO_ACT_CACHE"); return !ev || atoi(ev) != 0; }();
+  if (use_act_cache && h->pass_impl == METRPO_TRPO_PASS_AUTO && tiled_eligible(pd) && !pd.out_tanh) {
+    const size_t hid_rows = static_cast<size_t>(pd.sum_d - pd.d[0] - pd.d[pd.L]);
+    const size_t need = static_cast<size_t>((N + TILED_NT - 1) / TILED_NT) * hid_rows * TILED_NT;
+    if (need > h->act_cache_floats && need * 4 <= (static_cast<size_t>(8) << 30)) {
+      if (h->act_cache) { cudaStreamSynchronize(st); cudaFree(h->act_cache); h->act_cache = nullptr; h->act_cache_floats = 0; }
+      if (cudaMalloc(&h->act_cache, need * 4) == cudaSuccess) h->act_cache_floats = need;
+      else { h->act_cache = nullptr; cudaGetLastError(); }
+    }
+    if (hid_rows > 0 && need <= h->act_cache_floats) p.act_cache = h->act_cache;
+  }
+
   // loss_before and flat gradient g (one pass yields both)
   p.theta = theta;
   if ((rc = launch_pass<MODE_GRAD>(h, p, st)) != METRPO_OK) return rc;
@@ -1304,6 +1325,7 @@ extern "C" int metrpo_trpo_update(metrpo_trpo_t* h, long long N, const float* ob
 
   // back-tracking line search: ratio in backtrack_ratio ** arange(max_backtracks)
   p.vec = nullptr;
+  p.act_cache = nullptr;
   p.theta = h->trial_f;
   p.skip_flag = h->flags + FLAG_ACCEPTED;
   for (int k = 0; k < max_backtracks; ++k) {

@@ -220,6 +220,9 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
 
   double t_surr = 0.0, t_kl = 0.0, t_cnt = 0.0;
   const long long n_tiles = (p.N + NT - 1) / NT;
+  // hidden-activation cache (PassParams::act_cache): rows act_row[1] .. act_row[L]-1 of sAct, per tile
+  const int hid_rows = pd.sum_d - S - A;
+  const bool cached = (MODE != MODE_LOSS) && p.act_cache != nullptr && hid_rows > 0;
   const int obs_smp0 = tid / S, obs_f0 = tid - obs_smp0 * S, obs_dsmp = NT / S, obs_df = NT - obs_dsmp * S;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long n0 = tile * NT, ng = n0 + tid;
@@ -234,6 +237,14 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
         sAct[f * LD + smp] = (base + q < lim) ? p.obs[base + q] : 0.f;
         smp += obs_dsmp; f += obs_df;
         if (f >= S) { f -= S; ++smp; }
+      }
+    }
+    if (MODE == MODE_FVP && cached) {   // hidden activations of this tile, stored by the gradient pass
+      const float4* src = reinterpret_cast<const float4*>(p.act_cache + static_cast<size_t>(tile) * hid_rows * NT);
+      float* dst = sAct + pd.act_row[1] * LD;
+      for (int q = tid; q < hid_rows * (NT / 4); q += NT) {
+        const int r = q / (NT / 4), c4 = q - r * (NT / 4);
+        *reinterpret_cast<float4*>(dst + r * LD + 4 * c4) = __ldg(src + q);
       }
     }
     __syncthreads();
@@ -271,6 +282,14 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
       }
       __syncthreads();
     }
+    if (MODE == MODE_GRAD && cached) {
+      float4* dstc = reinterpret_cast<float4*>(p.act_cache + static_cast<size_t>(tile) * hid_rows * NT);
+      const float* srcc = sAct + pd.act_row[1] * LD;
+      for (int q = tid; q < hid_rows * (NT / 4); q += NT) {
+        const int r = q / (NT / 4), c4 = q - r * (NT / 4);
+        dstc[q] = *reinterpret_cast<const float4*>(srcc + r * LD + 4 * c4);
+      }
+    }
     const float* mu = mu_rows;
     float* cLs = sBufB;    // GRAD: per-sample d(-lr*adv)/d log_std_a, [A][LD]
 
@@ -289,7 +308,10 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
           float cf[8], c[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) { cf[j] = j < np ? sW[pd.sb_off[l] + j] : 0.f; c[j] = j < np ? sV[pd.sb_off[l] + j] : 0.f; }
-          sample_accum(cf, sAct + pd.act_row[l] * LD + tid, nin, sW + pd.sw_off[l], np);
+          // the layer's own activation: hidden layers take it from the cache when there is one, the
+          // last layer needs it only behind an output tanh
+          const bool need_fwd = last ? use_tanh : !cached;
+          if (need_fwd) sample_accum(cf, sAct + pd.act_row[l] * LD + tid, nin, sW + pd.sw_off[l], np);
           sample_accum(c, sAct + pd.act_row[l] * LD + tid, nin, sV + pd.sw_off[l], np);
           if (l > 0) sample_accum(c, tin + tid, nin, sW + pd.sw_off[l], np);
           float* aout = sAct + pd.act_row[l + 1] * LD + tid;
@@ -297,7 +319,7 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
           for (int j = 0; j < 8; ++j)
             if (j < nout) {
               float v = c[j];
-              const float av = use_tanh ? tanh_fast(cf[j]) : cf[j];
+              const float av = need_fwd ? (use_tanh ? tanh_fast(cf[j]) : cf[j]) : (last ? 0.f : aout[j * LD]);
               if (use_tanh) {
                 v *= (1.f - av * av);
                 if (last) v *= (1.f - av * av);   // back through the output tanh as well
@@ -319,7 +341,9 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
             cf[pp][0] = bw.x; cf[pp][1] = bw.y; cf[pp][2] = bw.z; cf[pp][3] = bw.w;
             c[pp][0] = b.x; c[pp][1] = b.y; c[pp][2] = b.z; c[pp][3] = b.w;
           }
-          tile_accum2(cf, c, sAct + pd.act_row[l] * LD + s0, nin, sW + pd.sw_off[l] + 4 * og, sV + pd.sw_off[l] + 4 * og, np);
+          const bool need_fwd = last ? use_tanh : !cached;
+          if (need_fwd) tile_accum2(cf, c, sAct + pd.act_row[l] * LD + s0, nin, sW + pd.sw_off[l] + 4 * og, sV + pd.sw_off[l] + 4 * og, np);
+          else tile_accum(c, sAct + pd.act_row[l] * LD + s0, nin, sV + pd.sw_off[l] + 4 * og, np);
           if (l > 0) tile_accum(c, tin + s0, nin, sW + pd.sw_off[l] + 4 * og, np);
           float* aout = sAct + pd.act_row[l + 1] * LD + s0;
 #pragma unroll
@@ -328,7 +352,12 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
               const int j = 4 * og + q;
               float v[8], av[8];
 #pragma unroll
-              for (int pp = 0; pp < 8; ++pp) { v[pp] = c[pp][q]; av[pp] = use_tanh ? tanh_fast(cf[pp][q]) : cf[pp][q]; }
+              for (int pp = 0; pp < 8; ++pp) { v[pp] = c[pp][q]; av[pp] = need_fwd ? (use_tanh ? tanh_fast(cf[pp][q]) : cf[pp][q]) : 0.f; }
+              if (!need_fwd && !last) {   // cached activation of this hidden unit
+                const float4 a0 = *reinterpret_cast<const float4*>(aout + j * LD);
+                const float4 a1 = *reinterpret_cast<const float4*>(aout + j * LD + 64);
+                av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+              }
               if (use_tanh) {
 #pragma unroll
                 for (int pp = 0; pp < 8; ++pp) v[pp] *= (1.f - av[pp] * av[pp]);
@@ -342,7 +371,7 @@ __global__ void __launch_bounds__(TILED_NT, 2) policy_pass_tiled_kernel(const __
                 const float m = 2.f / (2.f * __expf(2.f * ls) + 1e-8f);
 #pragma unroll
                 for (int pp = 0; pp < 8; ++pp) v[pp] *= m * sOk[(pp < 4 ? s0 : 60 + s0) + pp];
-              } else {
+              } else if (need_fwd) {
                 float4* a4 = reinterpret_cast<float4*>(aout + j * LD);
                 a4[0] = make_float4(av[0], av[1], av[2], av[3]);
                 a4[16] = make_float4(av[4], av[5], av[6], av[7]);
