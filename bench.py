@@ -83,12 +83,12 @@ def flops_per_step(spec, K, B, T, hidden):
     return K * B * T * f_dyn + B * T * f_pol
 
 
-def make_problem(seed=0, B=B_ROWS):
+def make_problem(seed=0, B=None):
     """Synthetic weights / states of the BASELINE shape: Xavier-uniform nets with the
     dynamics output layer scaled by 0.1 so that a 1000-step rollout of a random net stays finite.
     Product-side generator (me_trpo_b200/synthetic.py): the CUDA arm never imports oracle/."""
     from me_trpo_b200 import synthetic
-    return synthetic.make_problem(ENV, K_MODELS, B, hidden=HIDDEN, seed=seed)
+    return synthetic.make_problem(ENV, K_MODELS, B_ROWS if B is None else B, hidden=HIDDEN, seed=seed)
 
 
 class ClockSampler(threading.Thread):
