@@ -48,7 +48,7 @@ WORKLOADS = {
     "humanoid": ("humanoid", 20, 65536, 1000, 1024, 8),           # configs[4]
 }
 ENV, K_MODELS, B_ROWS, HORIZON, HIDDEN = "half-cheetah", 5, 4096, 1000, 1024
-E2E_CHUNKS = int(os.environ.get("METRPO_E2E_CHUNKS", "8"))
+E2E_CHUNKS = int(os.environ.get("METRPO_E2E_CHUNKS", "4"))
 
 
 def select_workload(args, world):

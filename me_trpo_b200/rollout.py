@@ -206,12 +206,12 @@ class EnsembleRollout:
         self._keep = self._keep[-8:] + [(pool, ep, mi, sn)]
         return out
 
-    def run_to_host(self, n_steps, init_states, reset_pool, host_out=None, dev_out=None, n_chunks=8,
+    def run_to_host(self, n_steps, init_states, reset_pool, host_out=None, dev_out=None, n_chunks=4,
                     eps=None, model_idx=None, std_noise=None, seed=0, offset=0, determ=False,
                     want=("obs", "act", "mean", "rew", "done")):
         """run() whose trajectory lands in pinned HOST buffers: the horizon is cut into n_chunks
         launches (metrpo_rollout_continue) and the device->host copy of chunk c runs on a second
-        stream while chunk c+1 is computed, so only the last chunk's copy is exposed.  Results are
+        stream while chunk c+1 is computed, so only the last (short) chunk's copy is exposed.  Results are
         identical to run().  Returns (host_out, dev_out); host buffers are valid after
         `synchronize()`."""
         dev, T, B, S, A = self.device, int(n_steps), self.B, self.S, self.A
@@ -235,7 +235,14 @@ class EnsembleRollout:
         main, side = torch.cuda.current_stream(dev), self._copy_stream
         side.wait_stream(main)          # earlier copies out of dev_out / into host_out are ordered
         n_chunks = max(1, min(int(n_chunks), T))
-        bounds = [round(i * T / n_chunks) for i in range(n_chunks + 1)]
+        # Only the LAST chunk's device->host copy is exposed (a chunk's copy is ~5x faster than its
+        # compute), so the tail is tapered: the last chunk is T/40 steps, the one before 3T/40, the rest equal.
+        tail = max(1, T // 40)
+        if n_chunks >= 3 and T - 4 * tail >= n_chunks - 2:
+            head = T - 4 * tail
+            bounds = [round(i * head / (n_chunks - 2)) for i in range(n_chunks - 1)] + [T - tail, T]
+        else:
+            bounds = [round(i * T / n_chunks) for i in range(n_chunks + 1)]
         sl = lambda t, a, b: None if t is None else t[a:b]
         for c in range(n_chunks):
             t0, t1 = bounds[c], bounds[c + 1]
