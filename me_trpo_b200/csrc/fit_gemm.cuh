@@ -60,6 +60,9 @@ struct GemmParams {
   int a_mn, b_mn;               // 1: operand stored MN-major ([k][m] / [k][n] row-major)
   int epi;
   int round_out;                // 1: round C to TF32-nearest (it is the operand of a later GEMM)
+  int splits;                   // split-K: blockIdx.z = model * splits + split; split s reduces its share of the K
+                                //   blocks into C + s * strideSplit (partials, summed by the caller; GEMM_EPI_PLAIN only)
+  long long strideSplit;
   int trans_store;              // 1: store C transposed, C[n * ldc + m], from registers (GEMM_EPI_PLAIN only)
   float* C; long long ldc, strideC;                     // ldc % 4 == 0 unless trans_store
   const float* bias; long long strideBias;              // GEMM_EPI_BIAS_RELU: bias[n] per model
@@ -137,8 +140,11 @@ fit_gemm_tf32_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool dbg_on = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   if (dbg_on && tid == 64) p.dbg[0] = globaltimer_ns();
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * Cfg::BM, model = blockIdx.z;
-  const int nkb = (p.Kd + GM_BK - 1) / GM_BK;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * Cfg::BM;
+  const int model = blockIdx.z / p.splits, split = blockIdx.z - model * p.splits;
+  const int nkb_all = (p.Kd + GM_BK - 1) / GM_BK;
+  const int kb_lo = static_cast<int>(static_cast<long long>(nkb_all) * split / p.splits);
+  const int nkb = static_cast<int>(static_cast<long long>(nkb_all) * (split + 1) / p.splits) - kb_lo;   // >= 1 (host: splits <= blocks)
   const int nch = min(Cfg::NCH, (p.N - n0 + 31) / 32);   // chunks of this tile that hold real columns
 
   if (tid == 0) {
@@ -167,10 +173,11 @@ fit_gemm_tf32_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA
         uint8_t* sA = sStage + s * Cfg::STAGE_BYTES;
         uint8_t* sB = sA + Cfg::A_BYTES;
         mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
-        if (p.a_mn) tma_load_4d(sA, &tmA, 0, kb * GM_BK, m0 / 32, model, &full[s]);
-        else        tma_load_4d(sA, &tmA, kb * GM_BK, m0, 0, model, &full[s]);
-        if (p.b_mn) tma_load_4d(sB, &tmB, 0, kb * GM_BK, n0 / 32, model, &full[s]);
-        else        tma_load_4d(sB, &tmB, kb * GM_BK, n0, 0, model, &full[s]);
+        const int k0 = (kb_lo + kb) * GM_BK;
+        if (p.a_mn) tma_load_4d(sA, &tmA, 0, k0, m0 / 32, model, &full[s]);
+        else        tma_load_4d(sA, &tmA, k0, m0, 0, model, &full[s]);
+        if (p.b_mn) tma_load_4d(sB, &tmB, 0, k0, n0 / 32, model, &full[s]);
+        else        tma_load_4d(sB, &tmB, k0, n0, 0, model, &full[s]);
         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
       }
       if (p.epi == GEMM_EPI_MASK) {
@@ -242,7 +249,7 @@ fit_gemm_tf32_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA
     const uint32_t tq = tmem + (static_cast<uint32_t>(q * 32) << 16);
     if (p.trans_store) {
       // thread = row m, register j = column: C[n][m] straight from registers, coalesced over lanes
-      float* Cm = p.C + model * p.strideC;
+      float* Cm = p.C + model * p.strideC + split * p.strideSplit;
       for (int mt = 0; mt < MT; ++mt) {
         const int m = m0 + mt * 128 + rl;
         for (int ch = par; ch < nch; ch += 2) {
@@ -333,7 +340,7 @@ fit_gemm_tf32_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA
         __syncwarp();
         if (lane == 0) {
           for (int ch = c_first; ch < c_hi; ch += 2) {
-            tma_store_4d(&tmC, sStage + (boff + ch) * GM_CHUNK_BYTES + q * 4096, n0 + ch * 32, mrow0, 0, model);
+            tma_store_4d(&tmC, sStage + (boff + ch) * GM_CHUNK_BYTES + q * 4096, n0 + ch * 32, mrow0, split, model);
             bulk_commit_group();
           }
           if (g == 0 && p.epi == GEMM_EPI_MASK && MT > 1 && nch > nhead) {
@@ -377,7 +384,7 @@ static PFN_tmapEncodeTiled fit_tmap_encoder() {
 // mn / kd: extents of the stored array (reads beyond them are zero-filled, stores are clipped).
 // Returns 0 on success.
 inline int fit_make_tmap(CUtensorMap* tm, const float* base, int mn_major, int mn, int kd, long long ld,
-                         int models, long long stride_model, int tile_mn) {
+                         int models, long long stride_model, int tile_mn, int splits = 1, long long stride_split = 0) {
   PFN_tmapEncodeTiled enc = fit_tmap_encoder();
   if (!enc) return -1;
   if ((ld & 3) || (stride_model & 3) || (reinterpret_cast<uintptr_t>(base) & 15)) return -2;
@@ -385,8 +392,11 @@ inline int fit_make_tmap(CUtensorMap* tm, const float* base, int mn_major, int m
   cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
   const cuuint64_t smodel = static_cast<cuuint64_t>(models > 1 ? stride_model : (long long)ld * (mn_major ? kd : mn)) * 4;
   if (!mn_major) {
-    dims[0] = kd; dims[1] = mn; dims[2] = 1; dims[3] = models;
-    strides[0] = static_cast<cuuint64_t>(ld) * 4; strides[1] = static_cast<cuuint64_t>(ld) * 4 * mn; strides[2] = smodel;
+    dims[0] = kd; dims[1] = mn; dims[2] = splits; dims[3] = models;   // dim 2: split-K partial (stores only)
+    strides[0] = static_cast<cuuint64_t>(ld) * 4;
+    strides[1] = splits > 1 ? static_cast<cuuint64_t>(stride_split) * 4 : static_cast<cuuint64_t>(ld) * 4 * mn;
+    strides[2] = smodel;
+    if (splits > 1 && (stride_split & 3)) return -2;
     box[0] = GM_BK; box[1] = tile_mn; box[2] = 1; box[3] = 1;
   } else {
     if (mn & 31) return -3;
@@ -417,9 +427,10 @@ static int fit_gemm_launch_t(const GemmParams& p, const GemmOperands& o, int mod
   if (r) return 2000 + r;
   tmC = tmA; tmAux = tmA;
   if (!p.trans_store) {
-    r = fit_make_tmap(&tmC, p.C, 0, p.M, p.N, p.ldc, models, p.strideC, 32);
+    r = fit_make_tmap(&tmC, p.C, 0, p.M, p.N, p.ldc, models, p.strideC, 32, p.splits, p.strideSplit);
     if (r) return 4000 + r;
   }
+  if (p.splits < 1 || (p.splits > 1 && p.epi != GEMM_EPI_PLAIN) || p.splits > (p.Kd + GM_BK - 1) / GM_BK) return 6000;
   if (p.epi == GEMM_EPI_MASK) {
     r = fit_make_tmap(&tmAux, o.aux, 0, p.M, p.N, o.ldaux, models, o.strideAux, 128);
     if (r) return 5000 + r;
@@ -431,7 +442,7 @@ static int fit_gemm_launch_t(const GemmParams& p, const GemmOperands& o, int mod
       return 3000;
     attr_set = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + Cfg::BM - 1) / Cfg::BM, models);
+  dim3 grid((p.N + BN - 1) / BN, (p.M + Cfg::BM - 1) / Cfg::BM, models * p.splits);
   fit_gemm_tf32_kernel<MT, BN><<<grid, GM_THREADS, Cfg::SMEM_BYTES, st>>>(p, tmA, tmB, tmC, tmAux);
   return 0;
 }

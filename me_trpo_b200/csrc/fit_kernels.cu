@@ -31,6 +31,7 @@
 namespace metrpo {
 
 constexpr uint32_t PHILOX_STREAM_FIT = 0x30000u;   // minibatch row indices
+constexpr int FIT_SPLITS = 3;   // split-K of the N <= 128 products when they would leave most SMs idle (40 CTAs at batch 1000)
 
 // per-step scalars of a replayed CUDA graph of the training iteration (device copy, refreshed before
 // every launch): kernels that take a `dargs` pointer read these instead of their by-value arguments
@@ -220,8 +221,8 @@ __global__ void fit_bias_relu_kernel(float* __restrict__ Hbuf, const float* __re
 __global__ void fit_mse_kernel(FitDims d, float* __restrict__ O, const float* __restrict__ XS,
                                const float* __restrict__ Y, const float* __restrict__ theta,
                                const float* __restrict__ norm, int rows, double inv_rows, int backward,
-                               long long strideS, long long strideO, double* __restrict__ loss_acc,
-                               float* __restrict__ part2) {
+                               long long strideS, long long strideO, int nsplit, long long strideSplit,
+                               double* __restrict__ loss_acc, float* __restrict__ part2) {
   const int k = blockIdx.y;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const float* b2 = theta + static_cast<size_t>(k) * d.P + d.ob2;
@@ -237,7 +238,9 @@ __global__ void fit_mse_kernel(FitDims d, float* __restrict__ O, const float* __
     for (int q = 0; q < 2; ++q) {
       const int s = lane + 32 * q;
       if (s < d.S) {
-        const float o = __fadd_rn(O[obase + s], b2[s]);
+        float osum = O[obase + s];                      // split-K partials of H1 W2, added in split order
+        for (int sp = 1; sp < nsplit; ++sp) osum = __fadd_rn(osum, O[sp * strideSplit + obase + s]);
+        const float o = __fadd_rn(osum, b2[s]);
         const float pred = __fadd_rn(__fadd_rn(dmean[s], __fmul_rn(dstd[s], o)), XS[base + s]);
         const float diff = __fsub_rn(pred, Y[base + s]);
         lsum += static_cast<double>(diff) * diff;
@@ -318,6 +321,8 @@ __global__ void fit_relu_bwd_colsum_kernel(float* __restrict__ dH, const float* 
 __global__ void __launch_bounds__(256) fit_bias_grad_finish_kernel(FitDims d, const float* __restrict__ part1,
                                                                    const float* __restrict__ part0, int nslab,
                                                                    const float* __restrict__ part2, int nblk2,
+                                                                   const float* __restrict__ w0part, int nsplit0,
+                                                                   long long w0_split_stride, long long w0_model_stride,
                                                                    float* __restrict__ grad) {
   __shared__ float red[8][33];
   const int k = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -328,10 +333,14 @@ __global__ void __launch_bounds__(256) fit_bias_grad_finish_kernel(FitDims d, co
   if (j < d.H) { p = part1 + static_cast<size_t>(k) * nslab * d.H + j; n = nslab; stride = d.H; out = d.ob1 + j; }
   else if (j < 2 * d.H) { p = part0 + static_cast<size_t>(k) * nslab * d.H + (j - d.H); n = nslab; stride = d.H; out = d.ob0 + j - d.H; }
   else if (j < 2 * d.H + d.S) { p = part2 + static_cast<size_t>(k) * nblk2 * d.S + (j - 2 * d.H); n = nblk2; stride = d.S; out = d.ob2 + j - 2 * d.H; }
+  else if (w0part != nullptr && j < 2 * d.H + d.S + d.Din * d.H) {   // dW0 = sum of its split-K partials
+    const int e0 = j - (2 * d.H + d.S);
+    p = w0part + static_cast<size_t>(k) * w0_model_stride + e0; n = nsplit0; stride = 0; out = d.oW0 + e0;
+  }
   float s = 0.f;
   if (p) {
 #pragma unroll 4
-    for (int b = ty; b < n; b += 8) s += p[static_cast<size_t>(b) * stride];
+    for (int b = ty; b < n; b += 8) s += (stride ? p[static_cast<size_t>(b) * stride] : p[static_cast<size_t>(b) * w0_split_stride]);
   }
   red[ty][tx] = s;
   __syncthreads();
@@ -409,6 +418,7 @@ struct metrpo_fit {
   float *Z = nullptr, *XS = nullptr, *Y = nullptr, *H0 = nullptr, *H1 = nullptr, *O = nullptr, *D1 = nullptr;
   float* norm = nullptr;
   float *part1 = nullptr, *part0 = nullptr, *part2 = nullptr;   // bias-gradient partials
+  float* w0part = nullptr;                                       // split-K partials of dW0: [FIT_SPLITS][K][up4(Din*H)]
   double* loss_acc = nullptr;
   float* min_losses = nullptr;
   uint8_t* flags = nullptr;
@@ -417,6 +427,7 @@ struct metrpo_fit {
   std::vector<char> w_set;
   int last_launches = 0;
   int nslab_max = 0;      // row slabs of the bias-gradient partial buffers
+  int o_splits = 1;       // split-K factor of the last forward's output-layer product (read by the MSE kernel)
   // backward pass: weight-gradient GEMMs run on a side stream next to the data-gradient GEMMs
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_w2 = nullptr, ev_d1 = nullptr, ev_join = nullptr;
@@ -440,7 +451,7 @@ static void fit_free(metrpo_fit* h) {
   for (cudaEvent_t e : {h->ev_fork, h->ev_w2, h->ev_d1, h->ev_join}) if (e) cudaEventDestroy(e);
   cudaFree(h->theta); cudaFree(h->grad); cudaFree(h->m); cudaFree(h->v); cudaFree(h->best);
   cudaFree(h->Z); cudaFree(h->XS); cudaFree(h->Y); cudaFree(h->H0); cudaFree(h->H1); cudaFree(h->O);
-  cudaFree(h->D1); cudaFree(h->norm); cudaFree(h->part1); cudaFree(h->part0); cudaFree(h->part2); cudaFree(h->loss_acc); cudaFree(h->min_losses); cudaFree(h->flags);
+  cudaFree(h->D1); cudaFree(h->norm); cudaFree(h->part1); cudaFree(h->part0); cudaFree(h->part2); cudaFree(h->w0part); cudaFree(h->loss_acc); cudaFree(h->min_losses); cudaFree(h->flags);
   delete h;
 }
 
@@ -495,7 +506,8 @@ extern "C" int metrpo_fit_create(const metrpo_fit_cfg* cfg, metrpo_fit_t** out) 
   alloc((void**)&h->v, PK); alloc((void**)&h->best, PK);
   alloc((void**)&h->Z, RK * d.Dp); alloc((void**)&h->XS, RK * d.S); alloc((void**)&h->Y, RK * d.S);
   alloc((void**)&h->H0, RK * d.H); alloc((void**)&h->H1, RK * d.H); alloc((void**)&h->D1, RK * d.H);
-  alloc((void**)&h->O, RK * d.Sp);
+  alloc((void**)&h->O, RK * d.Sp * FIT_SPLITS);                 // [FIT_SPLITS][K][R][Sp]: split-K partials of H1 W2
+  alloc((void**)&h->w0part, static_cast<size_t>(FIT_SPLITS) * d.K * ((d.Din * d.H + 3) / 4 * 4) * 4);
   alloc((void**)&h->norm, (2 * d.SA + 2 * d.S) * 4);
   const size_t nslab_max = static_cast<size_t>((h->R + 255) / 256) * 8;   // 32-row slabs of the GEMM epilogue
   h->nslab_max = static_cast<int>(nslab_max);
@@ -628,11 +640,13 @@ static int fit_check_ready(metrpo_fit* h, const char* who) {
 static int own_gemm(metrpo_fit* h, int M, int N, int Kd, const float* A, long long lda, long long sA, int a_mn,
                     int a_ext, const float* B, long long ldb, long long sB, int b_mn, int b_ext, float* C,
                     long long ldc, long long sC, int epi, const float* bias, const float* aux, float* colsum,
-                    int trans_store, cudaStream_t st, int a_kext = 0, int b_kext = 0) {
+                    int trans_store, cudaStream_t st, int a_kext = 0, int b_kext = 0, int splits = 1,
+                    long long strideSplit = 0) {
   GemmParams p;
   p.M = M; p.N = N; p.Kd = Kd; p.a_mn = a_mn; p.b_mn = b_mn; p.epi = epi; p.trans_store = trans_store;
   p.round_out = (epi != GEMM_EPI_PLAIN) ? 1 : 0;   // H1 / dH1 / dH0 feed later GEMMs
   p.C = C; p.ldc = ldc; p.strideC = sC; p.bias = bias; p.strideBias = h->d.P; p.colsum = colsum; p.dbg = nullptr;
+  p.splits = splits; p.strideSplit = strideSplit;
   GemmOperands o;
   o.A = A; o.lda = lda; o.strideA = sA; o.a_ext = a_ext; o.a_kext = a_kext;
   o.B = B; o.ldb = ldb; o.strideB = sB; o.b_ext = b_ext; o.b_kext = b_kext;
@@ -677,14 +691,17 @@ static int fit_forward(metrpo_fit* h, const float* x, const float* y, int n_data
                   GEMM_EPI_BIAS_RELU, h->theta + d.ob1, nullptr, nullptr, 0, st);
     if (rc != METRPO_OK) return rc;
     // O = H1 W2: B = W2 [k = H][n = Sp] MN-major (zero padded columns), 128-column tile
+    // (few row tiles: split the reduction over FIT_SPLITS CTAs per tile, the MSE kernel adds the partials)
+    h->o_splits = (((rows + 127) / 128) * d.K * FIT_SPLITS <= 160 && d.H / 32 >= 2 * FIT_SPLITS) ? FIT_SPLITS : 1;
     rc = own_gemm(h, rows, d.S, d.H, h->H1, d.H, sH, 0, rows, h->theta + d.oW2, d.Sp, P, 1, d.Sp, h->O, d.Sp, sO,
-                  GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 0, st);
+                  GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 0, st, 0, 0, h->o_splits, static_cast<long long>(d.K) * sO);
     if (rc != METRPO_OK) return rc;
     launches += 2;
   } else {
     METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.H, d.H, h->H0, d.H, sH, h->theta + d.oW1, d.H, P, h->H1, d.H, sH));
     fit_bias_relu_kernel<<<dim3(eb, d.K), 256, 0, st>>>(h->H1, h->theta, d.ob1, P, rows, d.H, sH);
     METRPO_BLAS_OK(gemm_rm(h, false, false, rows, d.S, d.H, h->H1, d.H, sH, h->theta + d.oW2, d.Sp, P, h->O, d.Sp, sO));
+    h->o_splits = 1;
     launches += 3;
   }
   METRPO_CUDA_OK(cudaGetLastError());
@@ -706,8 +723,10 @@ static int fit_step_issue(metrpo_fit* h, const float* x, const float* y, int n_d
   if (rc != METRPO_OK) return rc;
   const int mb = std::min((batch + 7) / 8, 148);
   fit_mse_kernel<<<dim3(mb, d.K), 256, 8 * d.S * 4, st>>>(d, h->O, h->XS, h->Y, h->theta, h->norm, batch, 1.0 / batch, 1,
-                                                     sS, sO, h->loss_acc, h->part2);
-  int nslab;
+                                                     sS, sO, h->o_splits, static_cast<long long>(d.K) * sO, h->loss_acc,
+                                                     h->part2);
+  int nslab, w0_splits = 1;
+  const long long P0 = (static_cast<long long>(d.Din) * d.H + 3) / 4 * 4;   // model stride of the dW0 partials
   if (own) {
     nslab = fit_gemm_colsum_slabs(batch, d.H);
     // The weight-gradient GEMMs (side stream) run next to the data-gradient GEMMs (caller's stream):
@@ -739,8 +758,14 @@ static int fit_step_issue(metrpo_fit* h, const float* x, const float* y, int n_d
     if (rc != METRPO_OK) return rc;
     // dW0[Din,H] = Z^T dH0, computed as its transpose (M = H fills the 128 tensor-core rows) and
     // stored transposed: A = dH0 [k = row][m = H] MN-major, B = Z [k = row][n = Dp] MN-major
-    rc = own_gemm(h, d.H, d.Din, batch, h->H1, d.H, sH, 1, d.H, h->Z, d.Dp, sZ, 1, d.Dp, h->grad + d.oW0, d.H, P,
-                  GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 1, st);
+    // (H / 128 row tiles x K models = 40 CTAs at H = 1024: split-K partials, summed with the bias gradients)
+    w0_splits = ((d.H + 127) / 128 * d.K * FIT_SPLITS <= 160 && (batch + 31) / 32 >= 2 * FIT_SPLITS) ? FIT_SPLITS : 1;
+    if (w0_splits > 1)
+      rc = own_gemm(h, d.H, d.Din, batch, h->H1, d.H, sH, 1, d.H, h->Z, d.Dp, sZ, 1, d.Dp, h->w0part, d.H, P0,
+                    GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 1, st, 0, 0, w0_splits, static_cast<long long>(d.K) * P0);
+    else
+      rc = own_gemm(h, d.H, d.Din, batch, h->H1, d.H, sH, 1, d.H, h->Z, d.Dp, sZ, 1, d.Dp, h->grad + d.oW0, d.H, P,
+                    GEMM_EPI_PLAIN, nullptr, nullptr, nullptr, 1, st);
     if (rc != METRPO_OK) return rc;
     METRPO_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join, 0));
     launches += 5;
@@ -758,8 +783,9 @@ static int fit_step_issue(metrpo_fit* h, const float* x, const float* y, int n_d
     METRPO_BLAS_OK(gemm_rm(h, true, false, d.Din, d.H, batch, h->Z, d.Dp, sZ, h->H1, d.H, sH, h->grad + d.oW0, d.H, P));
     launches += 7;
   }
-  fit_bias_grad_finish_kernel<<<dim3((2 * d.H + d.S + 31) / 32, d.K), 256, 0, st>>>(
-      d, h->part1, h->part0, nslab, h->part2, mb, h->grad);
+  fit_bias_grad_finish_kernel<<<dim3((2 * d.H + d.S + (w0_splits > 1 ? d.Din * d.H : 0) + 31) / 32, d.K), 256, 0, st>>>(
+      d, h->part1, h->part0, nslab, h->part2, mb, w0_splits > 1 ? h->w0part : nullptr, w0_splits,
+      static_cast<long long>(d.K) * P0, P0, h->grad);
   // Adam (tf.train.AdamOptimizer defaults beta1 0.9, beta2 0.999, epsilon 1e-8)
   const long long n4 = P * d.K / 4;
   fit_adam_kernel<<<static_cast<int>(std::min<long long>((n4 + 255) / 256, 148 * 8)), 256, 0, st>>>(
@@ -853,7 +879,8 @@ extern "C" int metrpo_fit_eval(metrpo_fit_t* h, const float* x, const float* y, 
     if (rc != METRPO_OK) return rc;
     const int mb = std::min((rows + 7) / 8, 148);
     fit_mse_kernel<<<dim3(mb, d.K), 256, 8 * d.S * 4, st>>>(d, h->O, h->XS, h->Y, h->theta, h->norm, rows, 1.0 / n, 0, sS,
-                                                       sO, h->loss_acc, h->part2);
+                                                       sO, h->o_splits, static_cast<long long>(d.K) * sO, h->loss_acc,
+                                                       h->part2);
     ++launches;
   }
   fit_snapshot_flags_kernel<<<1, 64, 0, st>>>(h->loss_acc, h->min_losses, h->flags, losses, d.K, snapshot);

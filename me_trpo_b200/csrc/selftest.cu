@@ -177,7 +177,7 @@ extern "C" int metrpo_dev_gemm_tf32(int M, int N, int Kd, int models, const floa
                                     long long ldaux, long long strideAux, float* dbg, void* stream_) {
   GemmParams p;
   p.dbg = reinterpret_cast<unsigned long long*>(dbg);
-  p.M = M; p.N = N; p.Kd = Kd; p.a_mn = a_mn; p.b_mn = b_mn; p.epi = epi; p.trans_store = 0; p.round_out = 0;
+  p.M = M; p.N = N; p.Kd = Kd; p.a_mn = a_mn; p.b_mn = b_mn; p.epi = epi; p.trans_store = 0; p.round_out = 0; p.splits = 1; p.strideSplit = 0;
   p.C = C; p.ldc = ldc; p.strideC = strideC; p.bias = bias; p.strideBias = strideBias; p.colsum = nullptr;
   GemmOperands o;
   o.A = A; o.lda = lda; o.strideA = strideA; o.a_ext = M; o.a_kext = 0;
