@@ -197,3 +197,30 @@ def test_graph_replay_equals_eager_iterations():
         for key in res["0"][0][m]:
             np.testing.assert_array_equal(res["0"][0][m][key], res["1"][0][m][key])
     np.testing.assert_allclose(np.array(res["0"][1]), np.array(res["1"][1]), rtol=1e-6)
+
+
+def test_train_steps_match_oracle_at_the_bench_shape():
+    """The shape bench.py's fit_iteration times (half-cheetah: K = 5 models, H = 1024, batch 1000, TF32
+    tcgen05 GEMMs with 256 x 256 tiles, split-K narrow products, side-stream wgrads) against the float32
+    NumPy oracle: same tolerances as the small shapes."""
+    S, A, drop, H, K, batch, steps = 18, 6, 1, 1024, 5, 1000, 3
+    models, norm, x, y = _problem(11, S, A, drop, H, K, n=4000)
+    fit = _fit(models, norm, S, A, drop, H, "tf32", max_rows=1024)
+    xd, yd = torch.as_tensor(x).cuda(), torch.as_tensor(y).cuda()
+    ref = [{k: v.copy() for k, v in m.items()} for m in models]
+    adam = of.Adam(ref)
+    rng = np.random.RandomState(3)
+    for j in range(steps):
+        idx = rng.randint(0, len(x), batch * K)
+        l_dev = fit.step(xd, yd, batch, 1e-3, idx=idx).cpu().numpy()
+        l_ref = of.train_step(ref, adam, norm, x, y, idx, batch, 1e-3, S, drop)
+        np.testing.assert_allclose(l_dev, l_ref, rtol=2e-3, atol=2e-3)
+    for k in range(K):
+        w = fit.get_weights(k)
+        for key in w:
+            d = w[key].cpu().numpy() - ref[k][key]
+            upd = ref[k][key] - models[k][key]
+            assert np.sqrt(np.mean(d ** 2)) <= 0.1 * np.sqrt(np.mean(upd ** 2)), key
+    vl = fit.eval(xd, yd)[0].cpu().numpy()
+    np.testing.assert_allclose(vl, of.validation_losses(ref, norm, x, y, S, drop), rtol=2e-3)
+    fit.close()
